@@ -255,6 +255,11 @@ int rtx_trace_rays_stats(rtx_ctx* ctx, const rtx_scene* scene, int64_t n, const 
  * world.hit queries issued. */
 int rtx_render(rtx_ctx* ctx, const rtx_scene* scene, const rtx_render_params* params,
                float* d_accum, unsigned long long* d_ray_count);
+/* Same render through the counting build of the kernel (slower; for roofline bookkeeping):
+ * synchronous, returns the number of world.hit queries in out->rays and the MEAN work per
+ * query in the other fields. */
+int rtx_render_counted(rtx_ctx* ctx, const rtx_scene* scene, const rtx_render_params* params,
+                       float* d_accum, rtx_trace_stats* out);
 /* mean, sqrt gamma, clamp(0,0.999)*256 -> u8, alpha 255 (src/main.rs:217-225).
  * d_accum: device float4 per pixel. out: RGBA8, host (out_on_device=0,
  * synchronous) or device (asynchronous). */
@@ -299,6 +304,12 @@ int rtx_builtin_scene_defaults(int scene_number, rtx_scene_defaults* out);
 int rtx_builtin_scene(int scene_number, uint64_t seed, const char* earth_png_path,
                       rtx_scene_desc** out);
 int rtx_scene_desc_free(rtx_scene_desc* desc);
+
+/* Host-only self check of the flattening step (no GPU): flattens `desc`, builds
+ * the BVHs and verifies that every record lies inside every ancestor box and is
+ * reachable exactly once. Outputs may be NULL. */
+int rtx_flatten_check(const rtx_scene_desc* desc, int32_t* n_bvh_nodes, int32_t* n_records,
+                      int32_t* n_prim_ids);
 
 /* PNG I/O (zlib based): 8-bit gray/RGB/RGBA(+alpha) non-interlaced decode to
  * RGBA8, RGBA8 encode (image::save_buffer, src/main.rs:231). */

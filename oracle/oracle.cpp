@@ -1184,19 +1184,20 @@ void orc_trace_rays(const orc_scene* s, int64_t n, const rtx_ray* rays, rtx_hit*
 }
 
 uint64_t orc_render(const orc_scene* s, int width, int height, int spp_begin, int spp_count, int max_depth, uint64_t seed,
-                    int row_begin, int row_end, double* rgb_sum, int n_threads) {
+                    int row_begin, int row_end, int row_stride, double* rgb_sum, int n_threads) {
     Camera camera(s->camera);
     std::atomic<uint64_t> total_rays{0};
     row_begin = std::max(0, row_begin);
     row_end = std::min(height, row_end);
-    int64_t n_rows = std::max(0, row_end - row_begin);
+    if (row_stride < 1) row_stride = 1;
+    int64_t n_rows = row_end > row_begin ? (row_end - row_begin + row_stride - 1) / row_stride : 0;
     run_parallel(n_threads, n_rows, 1, [&](int64_t b, int64_t e) {
         g_sampler = Sampler();
         g_sampler.fixed = false;
         g_sampler.key[0] = (uint32_t)seed;
         g_sampler.key[1] = (uint32_t)(seed >> 32);
         for (int64_t rr = b; rr < e; ++rr) {
-            int r = row_begin + (int)rr;       // row from the top (main.rs:202-204: rows are emitted top first)
+            int r = row_begin + (int)rr * row_stride;  // row from the top (main.rs:202-204: rows are emitted top first)
             int j = height - 1 - r;
             for (int i = 0; i < width; ++i) {
                 Vec3 acc;

@@ -50,10 +50,11 @@ void orc_trace_rays(const orc_scene* s, int64_t n, const rtx_ray* rays, rtx_hit*
  * per pixel to rgb_sum (width*height*3 doubles, row 0 = top). Randomness:
  * Philox4x32-10 keyed by seed, counter (pixel, sample, bounce|purpose, block) —
  * the same streams the CUDA kernels use. Returns the number of world.hit
- * queries. Rows [row_begin,row_end) only (for bounded CPU baselines). */
+ * queries. Only rows row_begin, row_begin + row_stride, ... < row_end are rendered (bounded
+ * CPU baselines sample every k-th row of the frame). */
 uint64_t orc_render(const orc_scene* s, int width, int height, int spp_begin, int spp_count,
-                    int max_depth, uint64_t seed, int row_begin, int row_end, double* rgb_sum,
-                    int n_threads);
+                    int max_depth, uint64_t seed, int row_begin, int row_end, int row_stride,
+                    double* rgb_sum, int n_threads);
 /* main.rs:217-225: mean, sqrt, clamp(0,0.999)*256 as u8, alpha 255. */
 void orc_tonemap(const double* rgb_sum, int n_pixels, double samples, uint8_t* rgba);
 

@@ -117,6 +117,7 @@ SIGNATURES = {
     "rtx_trace_rays_device": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "rtx_trace_rays_stats": (C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(TraceStats)]),
     "rtx_render": (C.c_int, [_P, _P, C.POINTER(RenderParams), _P, _P]),
+    "rtx_render_counted": (C.c_int, [_P, _P, C.POINTER(RenderParams), _P, C.POINTER(TraceStats)]),
     "rtx_tonemap_rgba8": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int]),
     "rtx_reduce_tonemap_peers": (C.c_int, [_P, _P, C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, _P]),
     "rtx_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
@@ -130,6 +131,8 @@ SIGNATURES = {
     "rtx_builtin_scene_defaults": (C.c_int, [C.c_int, C.POINTER(SceneDefaults)]),
     "rtx_builtin_scene": (C.c_int, [C.c_int, C.c_uint64, C.c_char_p, C.POINTER(C.POINTER(SceneDesc))]),
     "rtx_scene_desc_free": (C.c_int, [C.POINTER(SceneDesc)]),
+    "rtx_flatten_check": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32)]),
     "rtx_png_read_rgba8": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.POINTER(C.c_uint8))]),
     "rtx_png_write_rgba8": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _P]),

@@ -1,0 +1,528 @@
+// api.cu — the C ABI of include/rttnw_b200.h: contexts, scene upload, kernel launches.
+// No entry point computes on the CPU; without a CUDA device they fail with RTX_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rttnw_b200.h"
+#include "flatten.hpp"
+#include "kernels.cuh"
+#include "scene_api.hpp"
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return RTX_ERR_CUDA;
+}
+#define CU(call)                                      \
+    do {                                              \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+}  // namespace
+
+struct rtx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    unsigned int* d_work_counter = nullptr;  // render_kernel's tile dispenser
+    rtx::Counters* d_counters = nullptr;
+};
+
+struct rtx_scene {
+    rtx_ctx* ctx = nullptr;
+    rtx::SceneView view{};
+    rtx::CameraView camera{};
+    void* d_arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> textures;
+    int32_t n_nodes = 0, n_records = 0, n_xforms = 0;
+};
+
+extern "C" {
+
+int rtx_abi_version(void) { return RTX_ABI_VERSION; }
+const char* rtx_last_error(void) { return g_err.c_str(); }
+
+int rtx_device_count(int* count) {
+    if (!count) return fail(RTX_ERR_INVALID, "count is NULL");
+    *count = 0;
+    CU(cudaGetDeviceCount(count));
+    return RTX_OK;
+}
+
+int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
+    if (!out) return fail(RTX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(RTX_ERR_INVALID, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    rtx_ctx* c = new (std::nothrow) rtx_ctx();
+    if (!c) return fail(RTX_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaGetDeviceProperties"); }
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaMalloc(&c->d_work_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(rtx::Counters));
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc"); }
+    // the traversal stack lives in local memory: prefer L1 over shared for it
+    cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
+    cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
+    *out = c;
+    return RTX_OK;
+}
+
+int rtx_ctx_destroy(rtx_ctx* c) {
+    if (!c) return RTX_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_work_counter);
+    cudaFree(c->d_counters);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RTX_OK;
+}
+
+int rtx_ctx_sync(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return RTX_OK;
+}
+void* rtx_ctx_stream(rtx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- scene ----------------------------------------------------------------
+int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
+    if (!c || !desc || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    rtx::FlatScene fs;
+    std::string err;
+    if (!rtx::flatten_scene(*desc, fs, err)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    rtx_scene* s = new (std::nothrow) rtx_scene();
+    if (!s) return fail(RTX_ERR_NOMEM, "out of host memory");
+    s->ctx = c;
+    auto bail = [&](int code) { rtx_scene_destroy(s); return code; };
+
+    // images -> point-sampled texture objects (ImageTexture, texture.rs:61-107)
+    std::vector<rtx::DImage> dimages((size_t)desc->n_images);
+    for (int i = 0; i < desc->n_images; ++i) {
+        const rtx_image& im = desc->images[i];
+        rtx::DImage& di = dimages[(size_t)i];
+        di.tex = 0; di.width = im.width; di.height = im.height;
+        if (!im.rgba || im.width <= 0 || im.height <= 0) continue;
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        cudaError_t e = cudaMallocArray(&arr, &fmt, (size_t)im.width, (size_t)im.height);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocArray"));
+        s->arrays.push_back(arr);
+        e = cudaMemcpy2DToArrayAsync(arr, 0, 0, im.rgba, (size_t)im.width * 4, (size_t)im.width * 4, (size_t)im.height,
+                                     cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy2DToArray"));
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;  // nearest texel, no filtering, no sRGB decode (Q23)
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaCreateTextureObject"));
+        s->textures.push_back(tex);
+        di.tex = (unsigned long long)tex;
+    }
+
+    // one arena, every array 256-byte aligned
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off_nodes = 0;
+    size_t off_records = align(off_nodes + fs.nodes.size() * sizeof(rtx::BvhNode));
+    size_t off_xforms = align(off_records + fs.records.size() * sizeof(rtx::Record));
+    size_t off_mats = align(off_xforms + fs.xforms.size() * sizeof(rtx::XformOp));
+    size_t off_texs = align(off_mats + fs.materials.size() * sizeof(rtx::DMaterial));
+    size_t off_perlins = align(off_texs + fs.textures.size() * sizeof(rtx::DTexture));
+    size_t off_images = align(off_perlins + fs.perlins.size() * sizeof(rtx::DPerlin));
+    size_t total = align(off_images + dimages.size() * sizeof(rtx::DImage)) + 256;
+    std::vector<uint8_t> host(total, 0);
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(host.data() + off, src, bytes); };
+    put(off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(rtx::BvhNode));
+    put(off_records, fs.records.data(), fs.records.size() * sizeof(rtx::Record));
+    put(off_xforms, fs.xforms.data(), fs.xforms.size() * sizeof(rtx::XformOp));
+    put(off_mats, fs.materials.data(), fs.materials.size() * sizeof(rtx::DMaterial));
+    put(off_texs, fs.textures.data(), fs.textures.size() * sizeof(rtx::DTexture));
+    put(off_perlins, fs.perlins.data(), fs.perlins.size() * sizeof(rtx::DPerlin));
+    put(off_images, dimages.data(), dimages.size() * sizeof(rtx::DImage));
+    cudaError_t e = cudaMalloc(&s->d_arena, total);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scene)"));
+    s->arena_bytes = total;
+    e = cudaMemcpyAsync(s->d_arena, host.data(), total, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // `host` dies with this frame
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(scene)"));
+    uint8_t* base = (uint8_t*)s->d_arena;
+    s->view.nodes = (const rtx::BvhNode*)(base + off_nodes);
+    s->view.records = (const rtx::Record*)(base + off_records);
+    s->view.xforms = (const rtx::XformOp*)(base + off_xforms);
+    s->view.materials = (const rtx::DMaterial*)(base + off_mats);
+    s->view.textures = (const rtx::DTexture*)(base + off_texs);
+    s->view.perlins = (const rtx::DPerlin*)(base + off_perlins);
+    s->view.images = (const rtx::DImage*)(base + off_images);
+    s->view.world_root = fs.world_root;
+    s->view.n_media = fs.n_media;
+    s->camera = fs.camera;
+    s->n_nodes = (int32_t)fs.nodes.size();
+    s->n_records = (int32_t)fs.records.size();
+    s->n_xforms = (int32_t)fs.xforms.size();
+    *out = s;
+    return RTX_OK;
+}
+
+int rtx_scene_destroy(rtx_scene* s) {
+    if (!s) return RTX_OK;
+    if (s->ctx) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+    }
+    for (auto t : s->textures) cudaDestroyTextureObject(t);
+    for (auto a : s->arrays) cudaFreeArray(a);
+    if (s->d_arena) cudaFree(s->d_arena);
+    delete s;
+    return RTX_OK;
+}
+
+int rtx_scene_info(const rtx_scene* s, int32_t* n_bvh_nodes, int32_t* n_records, int32_t* n_xform_ops, int64_t* device_bytes) {
+    if (!s) return fail(RTX_ERR_INVALID, "scene is NULL");
+    if (n_bvh_nodes) *n_bvh_nodes = s->n_nodes;
+    if (n_records) *n_records = s->n_records;
+    if (n_xform_ops) *n_xform_ops = s->n_xforms;
+    if (device_bytes) *device_bytes = (int64_t)s->arena_bytes;
+    return RTX_OK;
+}
+
+// ---- fixed rays -------------------------------------------------------------
+int rtx_trace_rays_device(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ray* d_rays, rtx_hit* d_hits) {
+    if (!c || !s || n < 0 || (n > 0 && (!d_rays || !d_hits))) return fail(RTX_ERR_INVALID, "bad argument");
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(c->device));
+    const int block = 128;
+    int64_t grid = (n + block - 1) / block;
+    if (grid > 0x7fffffff) return fail(RTX_ERR_INVALID, "too many rays for one launch");
+    rtx::trace_rays_kernel<false><<<(unsigned)grid, block, 0, c->stream>>>(s->view, n, d_rays, d_hits, nullptr);
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+int rtx_trace_rays(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ray* rays, rtx_hit* hits) {
+    if (!c || !s || n < 0 || (n > 0 && (!rays || !hits))) return fail(RTX_ERR_INVALID, "bad argument");
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(c->device));
+    rtx_ray* d_rays = nullptr;
+    rtx_hit* d_hits = nullptr;
+    CU(cudaMalloc(&d_rays, (size_t)n * sizeof(rtx_ray)));
+    cudaError_t e = cudaMalloc(&d_hits, (size_t)n * sizeof(rtx_hit));
+    if (e != cudaSuccess) { cudaFree(d_rays); return cuda_fail(e, "cudaMalloc(hits)"); }
+    int rc = RTX_OK;
+    e = cudaMemcpyAsync(d_rays, rays, (size_t)n * sizeof(rtx_ray), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        rc = rtx_trace_rays_device(c, s, n, d_rays, d_hits);
+        if (rc == RTX_OK) {
+            e = cudaMemcpyAsync(hits, d_hits, (size_t)n * sizeof(rtx_hit), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        }
+    }
+    cudaFree(d_rays);
+    cudaFree(d_hits);
+    if (rc != RTX_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "rtx_trace_rays");
+    return RTX_OK;
+}
+
+int rtx_trace_rays_stats(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ray* d_rays, rtx_trace_stats* out) {
+    if (!c || !s || n <= 0 || !d_rays || !out) return fail(RTX_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(rtx::Counters), c->stream));
+    const int block = 128;
+    int64_t grid = (n + block - 1) / block;
+    if (grid > 0x7fffffff) return fail(RTX_ERR_INVALID, "too many rays for one launch");
+    rtx::trace_rays_kernel<true><<<(unsigned)grid, block, 0, c->stream>>>(s->view, n, d_rays, nullptr, c->d_counters);
+    CU(cudaGetLastError());
+    rtx::Counters h;
+    CU(cudaMemcpyAsync(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double dn = (double)n;
+    out->rays = dn;
+    out->box_tests = (double)h.box_tests / dn;
+    out->node_visits = (double)h.node_visits / dn;
+    out->sphere_tests = (double)h.sphere_tests / dn;
+    out->rect_tests = (double)h.rect_tests / dn;
+    out->instance_enters = (double)h.instance_enters / dn;
+    out->medium_tests = (double)h.medium_tests / dn;
+    return RTX_OK;
+}
+
+// ---- render -----------------------------------------------------------------
+static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum,
+                         unsigned long long* d_ray_count, bool counted) {
+    if (!c || !s || !p || !d_accum) return fail(RTX_ERR_INVALID, "NULL argument");
+    if (p->width <= 0 || p->height <= 0 || p->spp_count < 0 || p->spp_begin < 0 || p->max_depth < 0)
+        return fail(RTX_ERR_INVALID, "bad render parameters");
+    if ((int64_t)p->width * p->height > 0x7fffffff) return fail(RTX_ERR_INVALID, "image too large");
+    if (p->spp_count == 0) return RTX_OK;
+    CU(cudaSetDevice(c->device));
+    rtx::RenderArgs a;
+    a.sc = s->view;
+    a.cam = s->camera;
+    a.width = p->width; a.height = p->height;
+    a.spp_begin = p->spp_begin; a.spp_count = p->spp_count; a.max_depth = p->max_depth;
+    a.k0 = (uint32_t)p->seed; a.k1 = (uint32_t)(p->seed >> 32);
+    a.tiles_x = (p->width + rtx::kTileW - 1) / rtx::kTileW;
+    a.tiles_y = (p->height + rtx::kTileH - 1) / rtx::kTileH;
+    CU(cudaMemsetAsync(c->d_work_counter, 0, sizeof(unsigned int), c->stream));
+    // persistent grid: as many CTAs as fit, a whole number per SM
+    int per_sm = 0;
+    if (counted) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::render_kernel<true>, 128, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::render_kernel<false>, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t n_tiles = (int64_t)a.tiles_x * a.tiles_y;
+    int64_t grid = (int64_t)c->sm_count * per_sm;
+    int64_t needed = (n_tiles + 3) / 4;
+    if (grid > needed) grid = needed;
+    if (grid < 1) grid = 1;
+    float4* acc = reinterpret_cast<float4*>(d_accum);
+    if (counted)
+        rtx::render_kernel<true><<<(unsigned)grid, 128, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, c->d_counters);
+    else
+        rtx::render_kernel<false><<<(unsigned)grid, 128, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, nullptr);
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+int rtx_render(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum, unsigned long long* d_ray_count) {
+    return render_launch(c, s, p, d_accum, d_ray_count, false);
+}
+
+int rtx_render_counted(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum, rtx_trace_stats* out) {
+    if (!c || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    unsigned long long* d_rays = nullptr;
+    CU(cudaMalloc(&d_rays, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_rays, 0, sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, sizeof(rtx::Counters), c->stream);
+    int rc = e == cudaSuccess ? render_launch(c, s, p, d_accum, d_rays, true) : cuda_fail(e, "cudaMemset");
+    rtx::Counters h;
+    unsigned long long rays = 0;
+    if (rc == RTX_OK) {
+        e = cudaMemcpyAsync(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&rays, d_rays, sizeof(rays), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "rtx_render_counted");
+    }
+    cudaFree(d_rays);
+    if (rc != RTX_OK) return rc;
+    double dn = rays ? (double)rays : 1.0;
+    out->rays = (double)rays;
+    out->box_tests = (double)h.box_tests / dn;
+    out->node_visits = (double)h.node_visits / dn;
+    out->sphere_tests = (double)h.sphere_tests / dn;
+    out->rect_tests = (double)h.rect_tests / dn;
+    out->instance_enters = (double)h.instance_enters / dn;
+    out->medium_tests = (double)h.medium_tests / dn;
+    return RTX_OK;
+}
+
+int rtx_tonemap_rgba8(rtx_ctx* c, const float* d_accum, int32_t width, int32_t height, uint8_t* out, int out_on_device) {
+    if (!c || !d_accum || !out || width <= 0 || height <= 0) return fail(RTX_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    int n = width * height;
+    uchar4* d_out = (uchar4*)out;
+    if (!out_on_device) CU(cudaMalloc(&d_out, (size_t)n * 4));
+    rtx::tonemap_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(d_accum), n, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (!out_on_device) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_out);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "rtx_tonemap_rgba8");
+    return RTX_OK;
+}
+
+int rtx_reduce_tonemap_peers(rtx_ctx* c, float* d_accum, const float* const* d_peer_accums, int32_t n_peers, int32_t width,
+                             int32_t height, uint8_t* d_rgba8) {
+    if (!c || !d_accum || !d_rgba8 || width <= 0 || height <= 0 || n_peers < 0 || (n_peers > 0 && !d_peer_accums))
+        return fail(RTX_ERR_INVALID, "bad argument");
+    if (n_peers > rtx::kMaxPeers) return fail(RTX_ERR_UNSUPPORTED, "too many peers");
+    CU(cudaSetDevice(c->device));
+    rtx::PeerList pl;
+    pl.n = n_peers;
+    for (int i = 0; i < n_peers; ++i) {
+        pl.p[i] = reinterpret_cast<const float4*>(d_peer_accums[i]);
+        // same-process peers: make the other GPU's memory loadable from this one (IPC-opened
+        // pointers are already mapped by rtx_ipc_open)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, d_peer_accums[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+            at.device != c->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        }
+        cudaGetLastError();
+    }
+    int n = width * height;
+    rtx::reduce_tonemap_peers_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<float4*>(d_accum), pl, n,
+                                                                            reinterpret_cast<uchar4*>(d_rgba8));
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+// ---- memory / IPC helpers ------------------------------------------------------
+int rtx_malloc(rtx_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(out, bytes));
+    return RTX_OK;
+}
+int rtx_free(rtx_ctx* c, void* ptr) {
+    if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaFree(ptr));
+    return RTX_OK;
+}
+int rtx_memset_zero(rtx_ctx* c, void* ptr, size_t bytes) {
+    if (!c || !ptr) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(ptr, 0, bytes, c->stream));
+    return RTX_OK;
+}
+int rtx_memcpy_h2d(rtx_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RTX_OK;
+}
+int rtx_memcpy_d2h(rtx_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RTX_OK;
+}
+int rtx_ipc_export(rtx_ctx* c, void* d_ptr, uint8_t handle_out[64]) {
+    if (!c || !d_ptr || !handle_out) return fail(RTX_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle_out, &h, 64);
+    return RTX_OK;
+}
+int rtx_ipc_open(rtx_ctx* c, const uint8_t handle[64], void** d_ptr_out) {
+    if (!c || !handle || !d_ptr_out) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTX_OK;
+}
+int rtx_ipc_close(rtx_ctx* c, void* d_ptr) {
+    if (!c || !d_ptr) return fail(RTX_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return RTX_OK;
+}
+
+// ---- host-side mirrors (no GPU needed) -----------------------------------------
+int rtx_builtin_scene_defaults(int scene_number, rtx_scene_defaults* out) {
+    if (!out) return fail(RTX_ERR_INVALID, "out is NULL");
+    rttnw::SceneDefaults d;
+    if (!rttnw::builtin_scene_defaults(scene_number, d)) return fail(RTX_ERR_INVALID, "There is no scene " + std::to_string(scene_number));
+    out->width = d.width; out->height = d.height; out->samples = d.samples; out->max_depth = d.max_depth; out->name = d.name;
+    return RTX_OK;
+}
+
+struct DescBox {  // rtx_scene_desc must be the first member: the public pointer is &box->desc
+    rtx_scene_desc desc;
+    rttnw::SceneBuilder builder;
+};
+
+int rtx_builtin_scene(int scene_number, uint64_t seed, const char* earth_png_path, rtx_scene_desc** out) {
+    if (!out) return fail(RTX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    DescBox* box = new (std::nothrow) DescBox();
+    if (!box) return fail(RTX_ERR_NOMEM, "out of host memory");
+    if (!rttnw::builtin_scene(scene_number, seed, earth_png_path, box->builder)) {
+        delete box;
+        return fail(RTX_ERR_INVALID, "There is no scene " + std::to_string(scene_number));
+    }
+    box->desc = box->builder.desc;
+    *out = &box->desc;
+    return RTX_OK;
+}
+int rtx_scene_desc_free(rtx_scene_desc* desc) {
+    if (desc) delete reinterpret_cast<DescBox*>(desc);
+    return RTX_OK;
+}
+
+int rtx_flatten_check(const rtx_scene_desc* desc, int32_t* n_bvh_nodes, int32_t* n_records, int32_t* n_prim_ids) {
+    if (!desc) return fail(RTX_ERR_INVALID, "desc is NULL");
+    rtx::FlatScene fs;
+    std::string err;
+    if (!rtx::flatten_scene(*desc, fs, err)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    if (!rtx::check_flat_scene(fs, err)) return fail(RTX_ERR_INVALID, "flattened scene invariant violated: " + err);
+    if (n_bvh_nodes) *n_bvh_nodes = (int32_t)fs.nodes.size();
+    if (n_records) *n_records = (int32_t)fs.records.size();
+    if (n_prim_ids) *n_prim_ids = fs.n_prims;
+    return RTX_OK;
+}
+
+int rtx_png_read_rgba8(const char* path, int32_t* width, int32_t* height, uint8_t** rgba_out) {
+    if (!path || !width || !height || !rgba_out) return fail(RTX_ERR_INVALID, "NULL argument");
+    std::vector<uint8_t> px;
+    std::string err;
+    int w = 0, h = 0;
+    if (!rttnw::png_read_rgba8(path, w, h, px, err)) return fail(RTX_ERR_IO, err);
+    uint8_t* buf = (uint8_t*)std::malloc(px.size());
+    if (!buf) return fail(RTX_ERR_NOMEM, "out of host memory");
+    std::memcpy(buf, px.data(), px.size());
+    *width = w; *height = h; *rgba_out = buf;
+    return RTX_OK;
+}
+int rtx_png_write_rgba8(const char* path, int32_t width, int32_t height, const uint8_t* rgba) {
+    if (!path || !rgba) return fail(RTX_ERR_INVALID, "NULL argument");
+    std::string err;
+    if (!rttnw::png_write_rgba8(path, width, height, rgba, err)) return fail(RTX_ERR_IO, err);
+    return RTX_OK;
+}
+int rtx_buffer_free(void* p) {
+    std::free(p);
+    return RTX_OK;
+}
+
+}  // extern "C"

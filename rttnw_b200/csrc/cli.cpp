@@ -1,0 +1,127 @@
+// cli.cpp — `rttnw <scene>`: the reference's CLI (src/main.rs:236-258) on top of the C ABI.
+// Same positional argument, same usage text, same stdout lines, writes image.png (RGBA8) in the
+// CWD and reads assets/earth.png relative to it. Optional flags default to the reference values:
+//   --spp N  --width W  --height H  --seed S  --scene-seed S  --gpus N  --out PATH  --chunk N
+// With --gpus N one host thread drives each device; samples are sharded by global sample index
+// and rank 0 sums the peers' accumulators over peer-mapped memory in the tonemap kernel.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rttnw_b200.h"
+
+static void usage(const char* argv0) {  // main.rs:239-249
+    std::fprintf(stderr, "Usage: %s <scene>\n", argv0);
+    std::fprintf(stderr, "Possible scenes:\n");
+    static const char* names[] = {"random_scene", "two_spheres", "two_perlin_spheres", "earth", "simple_light",
+                                  "empty_cornell_box", "cornell_box", "smoke_cornell_box", "final_scene"};
+    for (int i = 0; i < 9; ++i) std::fprintf(stderr, "\t- %d: %s\n", i + 1, names[i]);
+}
+
+#define RTX(call)                                                            \
+    do {                                                                     \
+        if ((call) != RTX_OK) {                                              \
+            std::fprintf(stderr, "%s failed: %s\n", #call, rtx_last_error()); \
+            return 1;                                                        \
+        }                                                                    \
+    } while (0)
+
+struct Rank {
+    rtx_ctx* ctx = nullptr;
+    rtx_scene* scene = nullptr;
+    float* accum = nullptr;
+    int rc = 0;
+};
+
+int main(int argc, char** argv) {
+    int scene = -1, spp = -1, width = -1, height = -1, gpus = 1, chunk = 256;
+    unsigned long long seed = 1, scene_seed = 0;
+    bool have_scene_seed = false;
+    std::string out = "image.png";
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::fprintf(stderr, "%s needs a value\n", name); std::exit(1); }
+            return argv[++i];
+        };
+        if (a == "--spp") spp = std::atoi(next("--spp"));
+        else if (a == "--width") width = std::atoi(next("--width"));
+        else if (a == "--height") height = std::atoi(next("--height"));
+        else if (a == "--gpus") gpus = std::atoi(next("--gpus"));
+        else if (a == "--chunk") chunk = std::atoi(next("--chunk"));
+        else if (a == "--seed") seed = std::strtoull(next("--seed"), nullptr, 0);
+        else if (a == "--scene-seed") { scene_seed = std::strtoull(next("--scene-seed"), nullptr, 0); have_scene_seed = true; }
+        else if (a == "--out") out = next("--out");
+        else if (scene < 0 && !a.empty() && a[0] != '-') {
+            char* end = nullptr;
+            long v = std::strtol(a.c_str(), &end, 10);
+            if (*end != 0) { std::fprintf(stderr, "Error: There was an error\n"); return 1; }  // parse() failure -> DummyError
+            scene = (int)v;
+        } else { usage(argv[0]); std::fprintf(stderr, "Error: There was an error\n"); return 1; }
+    }
+    if (scene < 0) { usage(argv[0]); std::fprintf(stderr, "Error: There was an error\n"); return 1; }
+    std::printf("Scene number: %d\n", scene);
+    auto t0 = std::chrono::steady_clock::now();
+    rtx_scene_defaults def;
+    if (rtx_builtin_scene_defaults(scene, &def) != RTX_OK) {
+        std::fprintf(stderr, "%s\nError: There was an error\n", rtx_last_error());  // main.rs:179-182
+        return 1;
+    }
+    std::printf("Running scene %s\n", def.name);
+    if (spp < 0) spp = def.samples;
+    if (width < 0) width = def.width;
+    if (height < 0) height = def.height;
+    if (gpus < 1) gpus = 1;
+    if (chunk < 1) chunk = 1;
+    if (!have_scene_seed) scene_seed = 0x5254544E57ull + (unsigned long long)scene;
+    rtx_scene_desc* desc = nullptr;
+    RTX(rtx_builtin_scene(scene, scene_seed, nullptr, &desc));
+
+    std::vector<Rank> ranks((size_t)gpus);
+    auto worker = [&](int r) {
+        Rank& k = ranks[(size_t)r];
+        auto chk = [&](int rc) { if (rc != RTX_OK && k.rc == 0) { k.rc = rc; std::fprintf(stderr, "gpu %d: %s\n", r, rtx_last_error()); } return rc == RTX_OK; };
+        if (!chk(rtx_ctx_create(r, nullptr, &k.ctx))) return;
+        if (!chk(rtx_scene_create(k.ctx, desc, &k.scene))) return;
+        size_t bytes = (size_t)width * height * 4 * sizeof(float);
+        if (!chk(rtx_malloc(k.ctx, bytes, (void**)&k.accum))) return;
+        if (!chk(rtx_memset_zero(k.ctx, k.accum, bytes))) return;
+        int begin = (int)((long long)r * spp / gpus), end = (int)((long long)(r + 1) * spp / gpus);
+        for (int b = begin; b < end; b += chunk) {
+            rtx_render_params p;
+            std::memset(&p, 0, sizeof(p));
+            p.width = width; p.height = height; p.spp_begin = b; p.spp_count = (end - b < chunk) ? end - b : chunk;
+            p.max_depth = def.max_depth; p.seed = seed;
+            if (!chk(rtx_render(k.ctx, k.scene, &p, k.accum, nullptr))) return;
+        }
+        chk(rtx_ctx_sync(k.ctx));
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < gpus; ++r) th.emplace_back(worker, r);
+    for (auto& t : th) t.join();
+    for (auto& k : ranks) if (k.rc != 0) return 1;
+
+    // combine on rank 0: peers' accumulators are read over NVLink by the fused reduce+tonemap kernel
+    std::vector<uint8_t> rgba((size_t)width * height * 4);
+    uint8_t* d_rgba = nullptr;
+    RTX(rtx_malloc(ranks[0].ctx, rgba.size(), (void**)&d_rgba));
+    std::vector<const float*> peers;
+    for (int r = 1; r < gpus; ++r) peers.push_back(ranks[(size_t)r].accum);
+    RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.empty() ? nullptr : peers.data(), (int)peers.size(), width, height, d_rgba));
+    RTX(rtx_memcpy_d2h(ranks[0].ctx, rgba.data(), d_rgba, rgba.size()));
+    RTX(rtx_png_write_rgba8(out.c_str(), width, height, rgba.data()));  // image::save_buffer("image.png", ..), main.rs:231
+    rtx_free(ranks[0].ctx, d_rgba);
+    for (auto& k : ranks) {
+        rtx_free(k.ctx, k.accum);
+        rtx_scene_destroy(k.scene);
+        rtx_ctx_destroy(k.ctx);
+    }
+    rtx_scene_desc_free(desc);
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("%.6fs\n", secs);  // println!("{:?}", instant.elapsed())
+    return 0;
+}

@@ -1,0 +1,693 @@
+// flatten.cpp — scene description -> flat records, transform chains and SAH BVHs.
+//
+// What the reference does per ray (src/math/hittable.rs): List::hit scans every top-level
+// item (:153-163), wrappers Translate/YRotate re-express the ray (:599-605, :686-697) and
+// BvhTree::hit recurses through Arc<dyn Hittable> (:355-368). Here the same tree is turned,
+// once, into:
+//   * leaf records (sphere / moving sphere / rectangle; a Cube becomes its six rectangles
+//     in the order of Cube::new, :560-569),
+//   * one transform chain per distinct wrapper path (outermost op first),
+//   * a BVH per instanced group, one over the world (identity-chain primitives, instance
+//     records, medium records) and one per ConstantMedium boundary.
+// Bounds are geometrically correct rotated bounds — NOT YRotate::new's (:654-672),
+// which the reference never uses for culling either.
+#include "flatten.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace rtx {
+
+void Aabb::reset() {
+    for (int i = 0; i < 3; ++i) { lo[i] = INFINITY; hi[i] = -INFINITY; }
+}
+void Aabb::grow(const Aabb& o) {
+    for (int i = 0; i < 3; ++i) { lo[i] = std::fmin(lo[i], o.lo[i]); hi[i] = std::fmax(hi[i], o.hi[i]); }
+}
+void Aabb::grow_point(const double p[3]) {
+    for (int i = 0; i < 3; ++i) { lo[i] = std::fmin(lo[i], p[i]); hi[i] = std::fmax(hi[i], p[i]); }
+}
+double Aabb::half_area() const {
+    double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.0;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+namespace {
+
+struct Item {
+    Record rec;
+    Aabb box;
+    bool solo() const { return rec.type == REC_INSTANCE || rec.type == REC_MEDIUM; }  // must sit alone in its leaf
+};
+
+float round_down(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+float round_up(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+// ---------------------------------------------------------------------------
+// Binned-SAH BVH over a set of items; appends nodes and (reordered) records.
+// ---------------------------------------------------------------------------
+struct BvhBuilder {
+    std::vector<BvhNode>& nodes;
+    std::vector<Record>& records;
+    std::vector<Item>& items;
+    std::vector<int> order;
+    static constexpr int kBins = 16;
+    static constexpr int kMaxLeaf = 4;
+    static constexpr double kCostTraverse = 1.0;  // one 64-byte node fetch + two fp32 slab tests
+    static constexpr double kCostPrim = 2.0;      // one 96-byte record + an f64 intersection
+
+    struct Tmp {
+        Aabb box;
+        int left = -1, right = -1;
+        int first = 0, count = 0;
+    };
+    std::vector<Tmp> tmp;
+
+    BvhBuilder(std::vector<BvhNode>& n, std::vector<Record>& r, std::vector<Item>& it) : nodes(n), records(r), items(it) {}
+
+    int build_range(int lo, int hi) {
+        Tmp t;
+        t.box.reset();
+        Aabb cbox;
+        cbox.reset();
+        for (int i = lo; i < hi; ++i) {
+            const Aabb& b = items[(size_t)order[(size_t)i]].box;
+            t.box.grow(b);
+            double c[3] = {0.5 * (b.lo[0] + b.hi[0]), 0.5 * (b.lo[1] + b.hi[1]), 0.5 * (b.lo[2] + b.hi[2])};
+            cbox.grow_point(c);
+        }
+        t.first = lo;
+        t.count = hi - lo;
+        int n = hi - lo;
+        int self = (int)tmp.size();
+        tmp.push_back(t);
+        if (n <= 1) return self;
+        bool any_solo = false;
+        for (int i = lo; i < hi; ++i) any_solo = any_solo || items[(size_t)order[(size_t)i]].solo();
+
+        double best_cost = INFINITY;
+        int best_axis = -1, best_split = -1;
+        for (int axis = 0; axis < 3; ++axis) {
+            double cmin = cbox.lo[axis], cmax = cbox.hi[axis];
+            if (!(cmax > cmin)) continue;
+            Aabb bin_box[kBins];
+            int bin_n[kBins];
+            for (int b = 0; b < kBins; ++b) { bin_box[b].reset(); bin_n[b] = 0; }
+            double scale = kBins / (cmax - cmin);
+            for (int i = lo; i < hi; ++i) {
+                const Aabb& bx = items[(size_t)order[(size_t)i]].box;
+                double c = 0.5 * (bx.lo[axis] + bx.hi[axis]);
+                int b = std::min(kBins - 1, std::max(0, (int)((c - cmin) * scale)));
+                bin_box[b].grow(bx);
+                bin_n[b]++;
+            }
+            double right_area[kBins];
+            int right_n[kBins];
+            Aabb acc;
+            acc.reset();
+            int cnt = 0;
+            for (int b = kBins - 1; b >= 1; --b) {
+                acc.grow(bin_box[b]);
+                cnt += bin_n[b];
+                right_area[b] = acc.half_area();
+                right_n[b] = cnt;
+            }
+            acc.reset();
+            cnt = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                acc.grow(bin_box[b]);
+                cnt += bin_n[b];
+                if (cnt == 0 || right_n[b + 1] == 0) continue;
+                double cost = acc.half_area() * cnt + right_area[b + 1] * right_n[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = b; }
+            }
+        }
+        double area = t.box.half_area();
+        bool make_leaf = false;
+        if (any_solo) {
+            make_leaf = false;  // the traversal switches space / runs a sub-query on these: one per leaf
+        } else if (best_axis < 0) {
+            make_leaf = n <= kMaxLeaf;  // all centroids coincide
+        } else if (n <= kMaxLeaf) {
+            double split_cost = kCostTraverse + (area > 0 ? best_cost / area : 0.0) * kCostPrim;
+            make_leaf = n * kCostPrim <= split_cost;
+        }
+        if (make_leaf) return self;
+
+        int mid;
+        if (best_axis < 0) {
+            mid = lo + n / 2;  // degenerate: split the index range
+        } else {
+            double cmin = cbox.lo[best_axis], cmax = cbox.hi[best_axis];
+            double scale = kBins / (cmax - cmin);
+            auto it = std::partition(order.begin() + lo, order.begin() + hi, [&](int idx) {
+                const Aabb& bx = items[(size_t)idx].box;
+                double c = 0.5 * (bx.lo[best_axis] + bx.hi[best_axis]);
+                int b = std::min(kBins - 1, std::max(0, (int)((c - cmin) * scale)));
+                return b <= best_split;
+            });
+            mid = (int)(it - order.begin());
+            if (mid == lo || mid == hi) mid = lo + n / 2;
+        }
+        int l = build_range(lo, mid);
+        int r = build_range(mid, hi);
+        tmp[(size_t)self].left = l;
+        tmp[(size_t)self].right = r;
+        return self;
+    }
+
+    static void set_child_box(BvhNode& n, int which, const Aabb& b) {
+        float lo[3], hi[3];
+        for (int i = 0; i < 3; ++i) { lo[i] = round_down(b.lo[i]); hi[i] = round_up(b.hi[i]); }
+        if (which == 0) {
+            n.c0x[0] = lo[0]; n.c0x[1] = hi[0]; n.c0y[0] = lo[1]; n.c0y[1] = hi[1]; n.c0z[0] = lo[2]; n.c0z[1] = hi[2];
+        } else {
+            n.c1x[0] = lo[0]; n.c1x[1] = hi[0]; n.c1y[0] = lo[1]; n.c1y[1] = hi[1]; n.c1z[0] = lo[2]; n.c1z[1] = hi[2];
+        }
+    }
+    static void set_child_empty(BvhNode& n, int which) {
+        Aabb e;
+        for (int i = 0; i < 3; ++i) { e.lo[i] = FLT_MAX; e.hi[i] = -FLT_MAX; }
+        set_child_box(n, which, e);
+        (which == 0 ? n.child0 : n.child1) = kEmptyChild;
+    }
+    int32_t emit_leaf(const Tmp& t) {
+        int32_t first = (int32_t)records.size();
+        for (int i = 0; i < t.count; ++i) records.push_back(items[(size_t)order[(size_t)(t.first + i)]].rec);
+        return ~((first << 4) | t.count);
+    }
+    int32_t emit(int ti) {  // ti is an inner tmp node
+        int32_t idx = (int32_t)nodes.size();
+        nodes.push_back(BvhNode{});
+        int kids[2] = {tmp[(size_t)ti].left, tmp[(size_t)ti].right};
+        for (int k = 0; k < 2; ++k) {
+            const Tmp ct = tmp[(size_t)kids[k]];
+            int32_t ref = ct.left < 0 ? emit_leaf(ct) : emit(kids[k]);
+            BvhNode& n = nodes[(size_t)idx];
+            set_child_box(n, k, ct.box);
+            (k == 0 ? n.child0 : n.child1) = ref;
+        }
+        return idx;
+    }
+    // Returns the root node index; `bounds` gets the f64 bounds of everything.
+    int32_t build(Aabb& bounds) {
+        bounds.reset();
+        for (const auto& it : items) bounds.grow(it.box);
+        order.resize(items.size());
+        for (size_t i = 0; i < items.size(); ++i) order[i] = (int)i;
+        if (items.empty()) {
+            int32_t idx = (int32_t)nodes.size();
+            nodes.push_back(BvhNode{});
+            set_child_empty(nodes[(size_t)idx], 0);
+            set_child_empty(nodes[(size_t)idx], 1);
+            return idx;
+        }
+        int root = build_range(0, (int)items.size());
+        if (tmp[(size_t)root].left < 0) {  // the whole set is one leaf
+            int32_t idx = (int32_t)nodes.size();
+            nodes.push_back(BvhNode{});
+            int32_t ref = emit_leaf(tmp[(size_t)root]);
+            set_child_box(nodes[(size_t)idx], 0, tmp[(size_t)root].box);
+            nodes[(size_t)idx].child0 = ref;
+            set_child_empty(nodes[(size_t)idx], 1);
+            return idx;
+        }
+        return emit(root);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Tree walk
+// ---------------------------------------------------------------------------
+struct Group {
+    std::vector<XformOp> chain;
+    std::vector<Item> items;
+};
+struct World {
+    bool is_boundary = false;
+    std::vector<std::vector<int>> paths;  // insertion order; paths[0] is the identity path if present
+    std::map<std::vector<int>, Group> groups;
+    std::vector<Item> media;
+    Group& group(const std::vector<int>& path, const std::vector<XformOp>& chain) {
+        auto it = groups.find(path);
+        if (it == groups.end()) {
+            paths.push_back(path);
+            Group g;
+            g.chain = chain;
+            it = groups.emplace(path, std::move(g)).first;
+        }
+        return it->second;
+    }
+};
+
+struct Flattener {
+    const rtx_scene_desc& d;
+    FlatScene& out;
+    std::string& err;
+    std::vector<int> first_id;   // per node: first primitive id handed out, -1 = not visited
+    std::vector<int> medium_ord; // per MEDIUM node
+    int next_prim = 0, next_medium = 0;
+    double t_a = 0, t_b = 1;  // time interval moving-sphere bounds must cover
+
+    Flattener(const rtx_scene_desc& desc, FlatScene& o, std::string& e) : d(desc), out(o), err(e) {}
+
+    bool fail(const std::string& m) { err = m; return false; }
+
+    static void box_of_sphere(const double c[3], double r, Aabb& b) {
+        for (int i = 0; i < 3; ++i) { b.lo[i] = c[i] - std::fabs(r); b.hi[i] = c[i] + std::fabs(r); }
+    }
+
+    Item make_rect(int plane, double a0, double a1, double b0, double b1, double k, int material, int prim_id) {
+        Item it;
+        std::memset(&it.rec, 0, sizeof(it.rec));
+        it.rec.type = REC_RECT_XY + plane;
+        it.rec.a = material;
+        it.rec.b = prim_id;
+        it.rec.d[0] = a0; it.rec.d[1] = a1; it.rec.d[2] = b0; it.rec.d[3] = b1; it.rec.d[4] = k;
+        static const int ax0[3] = {0, 0, 1}, ax1[3] = {1, 2, 2}, axk[3] = {2, 1, 0};
+        // Rectangle::bounding_box pads k by 1e-4 (hittable.rs:532-546); ranges may be given reversed
+        it.box.lo[ax0[plane]] = std::fmin(a0, a1); it.box.hi[ax0[plane]] = std::fmax(a0, a1);
+        it.box.lo[ax1[plane]] = std::fmin(b0, b1); it.box.hi[ax1[plane]] = std::fmax(b0, b1);
+        it.box.lo[axk[plane]] = k - 0.0001; it.box.hi[axk[plane]] = k + 0.0001;
+        return it;
+    }
+
+    bool check_material(int m) { return m >= 0 && m < d.n_materials; }
+
+    bool collect(int ni, std::vector<int>& path, std::vector<XformOp>& chain, World& w, int depth) {
+        if (ni < 0 || ni >= d.n_nodes) return fail("node index out of range");
+        if (depth > 256) return fail("scene tree deeper than 256 (cycle?)");
+        const rtx_node& n = d.nodes[ni];
+        const double* f = n.f;
+        switch (n.kind) {
+            case RTX_NODE_SPHERE: {
+                if (!check_material(n.material)) return fail("sphere: bad material index");
+                if (first_id[(size_t)ni] < 0) first_id[(size_t)ni] = next_prim++;
+                Item it;
+                std::memset(&it.rec, 0, sizeof(it.rec));
+                it.rec.type = REC_SPHERE; it.rec.a = n.material; it.rec.b = first_id[(size_t)ni];
+                for (int i = 0; i < 4; ++i) it.rec.d[i] = f[i];
+                box_of_sphere(f, f[3], it.box);
+                w.group(path, chain).items.push_back(it);
+                return true;
+            }
+            case RTX_NODE_MOVING_SPHERE: {
+                if (!check_material(n.material)) return fail("moving sphere: bad material index");
+                if (first_id[(size_t)ni] < 0) first_id[(size_t)ni] = next_prim++;
+                Item it;
+                std::memset(&it.rec, 0, sizeof(it.rec));
+                it.rec.type = REC_MSPHERE; it.rec.a = n.material; it.rec.b = first_id[(size_t)ni];
+                double r = f[6], t0 = f[7], t1 = f[8];
+                for (int i = 0; i < 3; ++i) { it.rec.d[i] = f[i]; it.rec.d[3 + i] = f[3 + i] - f[i]; }
+                it.rec.d[6] = r; it.rec.d[7] = t0; it.rec.d[8] = 1.0 / (t1 - t0);
+                // MovingSphere::bounding_box (hittable.rs:233-244) over the shutter interval
+                it.box.reset();
+                const double ts[2] = {t_a, t_b};
+                for (double t : ts) {
+                    double c[3];
+                    for (int i = 0; i < 3; ++i) c[i] = f[i] + ((t - t0) / (t1 - t0)) * (f[3 + i] - f[i]);
+                    Aabb b;
+                    box_of_sphere(c, r, b);
+                    it.box.grow(b);
+                }
+                w.group(path, chain).items.push_back(it);
+                return true;
+            }
+            case RTX_NODE_RECT_XY:
+            case RTX_NODE_RECT_XZ:
+            case RTX_NODE_RECT_YZ: {
+                if (!check_material(n.material)) return fail("rectangle: bad material index");
+                if (first_id[(size_t)ni] < 0) first_id[(size_t)ni] = next_prim++;
+                w.group(path, chain).items.push_back(
+                    make_rect(n.kind - RTX_NODE_RECT_XY, f[0], f[1], f[2], f[3], f[4], n.material, first_id[(size_t)ni]));
+                return true;
+            }
+            case RTX_NODE_CUBE: {
+                if (!check_material(n.material)) return fail("cube: bad material index");
+                if (first_id[(size_t)ni] < 0) { first_id[(size_t)ni] = next_prim; next_prim += 6; }
+                int id = first_id[(size_t)ni];
+                Group& g = w.group(path, chain);
+                // Cube::new, hittable.rs:560-569 with Plane::points :451-479
+                g.items.push_back(make_rect(0, f[0], f[3], f[1], f[4], f[2], n.material, id + 0));
+                g.items.push_back(make_rect(0, f[0], f[3], f[1], f[4], f[5], n.material, id + 1));
+                g.items.push_back(make_rect(1, f[0], f[3], f[2], f[5], f[1], n.material, id + 2));
+                g.items.push_back(make_rect(1, f[0], f[3], f[2], f[5], f[4], n.material, id + 3));
+                g.items.push_back(make_rect(2, f[1], f[4], f[2], f[5], f[0], n.material, id + 4));
+                g.items.push_back(make_rect(2, f[1], f[4], f[2], f[5], f[3], n.material, id + 5));
+                return true;
+            }
+            case RTX_NODE_LIST:
+            case RTX_NODE_BVH: {
+                if (n.n_children < 0 || n.child < 0 || n.child + n.n_children > d.n_children) return fail("list: bad children range");
+                for (int c = 0; c < n.n_children; ++c)
+                    if (!collect(d.children[n.child + c], path, chain, w, depth + 1)) return false;
+                return true;
+            }
+            case RTX_NODE_TRANSLATE:
+            case RTX_NODE_ROTATE_Y: {
+                XformOp op;
+                std::memset(&op, 0, sizeof(op));
+                if (n.kind == RTX_NODE_TRANSLATE) {
+                    op.kind = XF_TRANSLATE;
+                    op.v[0] = f[0]; op.v[1] = f[1]; op.v[2] = f[2];
+                } else {
+                    op.kind = XF_ROTATE_Y;
+                    const double PI = 3.14159265358979323846;
+                    double radians = f[0] * (PI / 180.0);  // f64::to_radians, hittable.rs:641-643
+                    op.v[0] = std::sin(radians);
+                    op.v[1] = std::cos(radians);
+                }
+                if (chain.size() >= 16) return fail("more than 16 nested translate/rotate_y wrappers");
+                path.push_back(ni);
+                chain.push_back(op);
+                bool ok = collect(n.child, path, chain, w, depth + 1);
+                path.pop_back();
+                chain.pop_back();
+                return ok;
+            }
+            case RTX_NODE_MEDIUM: {
+                if (w.is_boundary) return fail("ConstantMedium inside a ConstantMedium boundary is not supported");
+                if (n.material < 0 || n.material >= d.n_textures) return fail("medium: bad phase texture index");
+                if (!(f[0] != 0.0)) return fail("medium: density must be non-zero");
+                World bw;
+                bw.is_boundary = true;
+                if (!collect(n.child, path, chain, bw, depth + 1)) return false;
+                if (first_id[(size_t)ni] < 0) {
+                    first_id[(size_t)ni] = next_prim++;
+                    medium_ord[(size_t)ni] = next_medium++;
+                }
+                Aabb bounds;
+                Item it;
+                std::memset(&it.rec, 0, sizeof(it.rec));
+                // The common case (scenes.rs:282-301): the boundary is one untransformed Sphere. Its two
+                // boundary.hit() calls (hittable.rs:745-752) then reduce to the two roots of one quadratic.
+                const Group* only = (bw.paths.size() == 1 && bw.paths[0].empty() && bw.media.empty()) ? &bw.groups[bw.paths[0]] : nullptr;
+                int32_t root = -1;
+                if (only && only->items.size() == 1 && only->items[0].rec.type == REC_SPHERE && chain.empty()) {
+                    for (int i = 0; i < 4; ++i) it.rec.d[4 + i] = only->items[0].rec.d[i];
+                    bounds = only->items[0].box;
+                } else {
+                    root = build_world(bw, bounds);
+                }
+                it.rec.type = REC_MEDIUM;
+                it.rec.a = n.material;
+                it.rec.b = first_id[(size_t)ni];
+                it.rec.c = root;
+                it.rec.d[0] = -1.0 / f[0];  // ConstantMedium::new, hittable.rs:731-735
+                it.rec.d[1] = (double)medium_ord[(size_t)ni];
+                it.rec.d[2] = (double)out.xforms.size();
+                it.rec.d[3] = (double)chain.size();
+                for (const auto& op : chain) out.xforms.push_back(op);
+                it.box = bounds;
+                w.media.push_back(it);
+                return true;
+            }
+            default:
+                return fail("unknown node kind");
+        }
+    }
+
+    // object -> world: undo the chain, innermost op first
+    static void to_world(const std::vector<XformOp>& chain, double p[3]) {
+        for (size_t i = chain.size(); i-- > 0;) {
+            const XformOp& op = chain[i];
+            if (op.kind == XF_TRANSLATE) {
+                p[0] += op.v[0]; p[1] += op.v[1]; p[2] += op.v[2];
+            } else {
+                double s = op.v[0], c = op.v[1];
+                double x = c * p[0] + s * p[2];
+                double z = -s * p[0] + c * p[2];
+                p[0] = x; p[2] = z;
+            }
+        }
+    }
+
+    int32_t build_world(World& w, Aabb& bounds) {
+        std::vector<Item> top;
+        for (const auto& path : w.paths) {
+            Group& g = w.groups[path];
+            if (path.empty()) {
+                for (auto& it : g.items) top.push_back(it);
+                continue;
+            }
+            Aabb ob;
+            BvhBuilder b(out.nodes, out.records, g.items);
+            int32_t root = b.build(ob);
+            Item inst;
+            std::memset(&inst.rec, 0, sizeof(inst.rec));
+            inst.rec.type = REC_INSTANCE;
+            inst.rec.a = root;
+            inst.rec.b = (int32_t)g.chain.size();
+            inst.rec.c = (int32_t)out.xforms.size();
+            for (const auto& op : g.chain) out.xforms.push_back(op);
+            inst.box.reset();
+            if (!g.items.empty()) {
+                for (int corner = 0; corner < 8; ++corner) {
+                    double p[3] = {(corner & 1) ? ob.hi[0] : ob.lo[0], (corner & 2) ? ob.hi[1] : ob.lo[1],
+                                   (corner & 4) ? ob.hi[2] : ob.lo[2]};
+                    to_world(g.chain, p);
+                    inst.box.grow_point(p);
+                }
+                // rotation arithmetic rounds: pad by a few ulps of the extent
+                for (int i = 0; i < 3; ++i) {
+                    double pad = 1e-12 * std::fmax(1.0, std::fmax(std::fabs(inst.box.lo[i]), std::fabs(inst.box.hi[i])));
+                    inst.box.lo[i] -= pad; inst.box.hi[i] += pad;
+                }
+            }
+            top.push_back(inst);
+        }
+        for (auto& m : w.media) top.push_back(m);
+        BvhBuilder b(out.nodes, out.records, top);
+        return b.build(bounds);
+    }
+
+    bool run() {
+        if (!d.nodes || d.n_nodes <= 0) return fail("scene has no nodes");
+        if (d.root < 0 || d.root >= d.n_nodes) return fail("root index out of range");
+        first_id.assign((size_t)d.n_nodes, -1);
+        medium_ord.assign((size_t)d.n_nodes, -1);
+        t_a = std::fmin(0.0, d.camera.open_time);
+        t_b = std::fmax(1.0, d.camera.close_time);
+        // materials / textures / perlin tables in device precision
+        out.materials.resize((size_t)d.n_materials);
+        for (int i = 0; i < d.n_materials; ++i) {
+            const rtx_material& m = d.materials[i];
+            DMaterial& o = out.materials[(size_t)i];
+            std::memset(&o, 0, sizeof(o));
+            if (m.kind < RTX_MAT_LAMBERTIAN || m.kind > RTX_MAT_ISOTROPIC) return fail("unknown material kind");
+            bool needs_tex = m.kind == RTX_MAT_LAMBERTIAN || m.kind == RTX_MAT_DIFFUSE_LIGHT || m.kind == RTX_MAT_ISOTROPIC;
+            if (needs_tex && (m.texture < 0 || m.texture >= d.n_textures)) return fail("material: bad texture index");
+            o.kind = m.kind;
+            o.texture = m.texture;
+            for (int c = 0; c < 3; ++c) o.albedo[c] = (float)m.albedo[c];
+            o.param = (float)(m.kind == RTX_MAT_METAL ? std::fmin(m.param, 1.0) : m.param);  // material.rs:126-131
+        }
+        out.textures.resize((size_t)d.n_textures);
+        for (int i = 0; i < d.n_textures; ++i) {
+            const rtx_texture& t = d.textures[i];
+            DTexture& o = out.textures[(size_t)i];
+            std::memset(&o, 0, sizeof(o));
+            o.kind = t.kind; o.a = t.a; o.b = t.b;
+            for (int c = 0; c < 4; ++c) o.f[c] = (float)t.f[c];
+            switch (t.kind) {
+                case RTX_TEX_SOLID: break;
+                case RTX_TEX_CHECKER:
+                    if (t.a < 0 || t.a >= d.n_textures || t.b < 0 || t.b >= d.n_textures) return fail("checker: bad child texture");
+                    break;
+                case RTX_TEX_NOISE:
+                    if (t.a < 0 || t.a >= d.n_perlins) return fail("noise: bad perlin index");
+                    break;
+                case RTX_TEX_IMAGE:
+                    if (t.a < 0 || t.a >= d.n_images) return fail("image texture: bad image index");
+                    break;
+                default: return fail("unknown texture kind");
+            }
+        }
+        // _pad = 1 when evaluating the texture needs the surface (u, v): images, and checkers over them
+        for (int pass = 0; pass < 8; ++pass)
+            for (int i = 0; i < d.n_textures; ++i) {
+                DTexture& o = out.textures[(size_t)i];
+                if (o.kind == RTX_TEX_IMAGE) o._pad = 1;
+                if (o.kind == RTX_TEX_CHECKER) o._pad = out.textures[(size_t)o.a]._pad | out.textures[(size_t)o.b]._pad;
+            }
+        out.perlins.resize((size_t)d.n_perlins);
+        for (int i = 0; i < d.n_perlins; ++i) {
+            const rtx_perlin& p = d.perlins[i];
+            DPerlin& o = out.perlins[(size_t)i];
+            for (int k = 0; k < 256; ++k) {
+                o.ranvec[k][0] = (float)p.ranvec[k][0]; o.ranvec[k][1] = (float)p.ranvec[k][1];
+                o.ranvec[k][2] = (float)p.ranvec[k][2]; o.ranvec[k][3] = 0.f;
+                o.perm[0][k] = (uint8_t)(p.perm_x[k] & 255); o.perm[1][k] = (uint8_t)(p.perm_y[k] & 255);
+                o.perm[2][k] = (uint8_t)(p.perm_z[k] & 255);
+            }
+        }
+        World w;
+        std::vector<int> path;
+        std::vector<XformOp> chain;
+        if (!collect(d.root, path, chain, w, 0)) return false;
+        out.world_root = build_world(w, out.world_bounds);
+        out.n_media = next_medium;
+        out.n_prims = next_prim;
+        camera_view(d.camera, d.background, out.camera);
+        return true;
+    }
+};
+
+}  // namespace
+
+bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err) {
+    out = FlatScene();
+    Flattener f(desc, out, err);
+    return f.run();
+}
+
+// Camera::new, src/math/camera.rs:32-61, evaluated once on the host in f64.
+void camera_view(const rtx_camera& d, const double background[3], CameraView& o) {
+    const double PI = 3.14159265358979323846;
+    auto sub = [](const double a[3], const double b[3], double r[3]) { for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i]; };
+    auto cross = [](const double a[3], const double b[3], double r[3]) {  // vec3.rs:82-88
+        r[0] = a[1] * b[2] - a[2] * b[1];
+        r[1] = -(a[0] * b[2] - a[2] * b[0]);
+        r[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto unit = [](double v[3]) {
+        double k = 1.0 / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        for (int i = 0; i < 3; ++i) v[i] *= k;
+    };
+    o.lens_radius = d.aperture / 2.0;
+    double theta = d.vertical_fov * PI / 180.0;
+    double half_height = std::tan(theta / 2.0);
+    double half_width = d.aspect_ratio * half_height;
+    double w[3], u[3], v[3];
+    sub(d.lookfrom, d.lookat, w);
+    unit(w);
+    cross(d.view_up, w, u);
+    unit(u);
+    cross(w, u, v);
+    for (int i = 0; i < 3; ++i) {
+        o.origin[i] = d.lookfrom[i];
+        o.u[i] = u[i]; o.v[i] = v[i];
+        o.lower_left[i] = d.lookfrom[i] - half_width * d.focus_distance * u[i] - half_height * d.focus_distance * v[i] -
+                          d.focus_distance * w[i];
+        o.horizontal[i] = 2.0 * half_width * d.focus_distance * u[i];
+        o.vertical[i] = 2.0 * half_height * d.focus_distance * v[i];
+        o.background[i] = (float)background[i];
+    }
+    o.time0 = d.open_time;
+    o.time1 = d.close_time;
+}
+
+// ---------------------------------------------------------------------------
+// Invariant checker (host logic tests): every BVH reachable from the world root
+// (through instance and medium records) must contain its records.
+// ---------------------------------------------------------------------------
+namespace {
+struct Checker {
+    const FlatScene& fs;
+    std::string& err;
+    std::vector<int> node_seen, rec_seen;
+    bool fail(const std::string& m) { err = m; return false; }
+
+    static bool inside(const float lo[3], const float hi[3], const Aabb& b) {
+        for (int i = 0; i < 3; ++i)
+            if (!((double)lo[i] <= b.lo[i] && (double)hi[i] >= b.hi[i])) return false;
+        return true;
+    }
+    bool record_box(const Record& r, Aabb& b) {
+        b.reset();
+        static const int ax0[3] = {0, 0, 1}, ax1[3] = {1, 2, 2}, axk[3] = {2, 1, 0};
+        switch (r.type) {
+            case REC_SPHERE:
+                for (int i = 0; i < 3; ++i) { b.lo[i] = r.d[i] - std::fabs(r.d[3]); b.hi[i] = r.d[i] + std::fabs(r.d[3]); }
+                return true;
+            case REC_MSPHERE:
+                for (int i = 0; i < 3; ++i) {  // at its own t0 (a point the bounds must contain when t0 is in the shutter)
+                    b.lo[i] = r.d[i] - std::fabs(r.d[6]); b.hi[i] = r.d[i] + std::fabs(r.d[6]);
+                }
+                return true;
+            case REC_RECT_XY: case REC_RECT_XZ: case REC_RECT_YZ: {
+                int p = r.type - REC_RECT_XY;
+                b.lo[ax0[p]] = std::fmin(r.d[0], r.d[1]); b.hi[ax0[p]] = std::fmax(r.d[0], r.d[1]);
+                b.lo[ax1[p]] = std::fmin(r.d[2], r.d[3]); b.hi[ax1[p]] = std::fmax(r.d[2], r.d[3]);
+                b.lo[axk[p]] = r.d[4]; b.hi[axk[p]] = r.d[4];
+                return true;
+            }
+            default: return false;  // instance / medium: checked through their own BVH
+        }
+    }
+    // returns the union of the float boxes of the subtree through `bounds_lo/hi`
+    bool walk(int32_t ni, int depth, int& n_records) {
+        if (ni < 0 || ni >= (int32_t)fs.nodes.size()) return fail("node index out of range");
+        if (depth > 128) return fail("BVH deeper than 128");
+        if (node_seen[(size_t)ni]++) return fail("node reachable twice");
+        const BvhNode& n = fs.nodes[(size_t)ni];
+        for (int k = 0; k < 2; ++k) {
+            int32_t ref = k == 0 ? n.child0 : n.child1;
+            float lo[3] = {k == 0 ? n.c0x[0] : n.c1x[0], k == 0 ? n.c0y[0] : n.c1y[0], k == 0 ? n.c0z[0] : n.c1z[0]};
+            float hi[3] = {k == 0 ? n.c0x[1] : n.c1x[1], k == 0 ? n.c0y[1] : n.c1y[1], k == 0 ? n.c0z[1] : n.c1z[1]};
+            if (ref >= 0) {
+                // child inner node: both of ITS child boxes must lie inside this box
+                const BvhNode& c = fs.nodes[(size_t)ref];
+                const float* cl[2][3] = {{&c.c0x[0], &c.c0y[0], &c.c0z[0]}, {&c.c1x[0], &c.c1y[0], &c.c1z[0]}};
+                const float* ch[2][3] = {{&c.c0x[1], &c.c0y[1], &c.c0z[1]}, {&c.c1x[1], &c.c1y[1], &c.c1z[1]}};
+                for (int j = 0; j < 2; ++j) {
+                    if ((j == 0 ? c.child0 : c.child1) == kEmptyChild) continue;
+                    for (int i = 0; i < 3; ++i)
+                        if (!(*cl[j][i] >= lo[i] && *ch[j][i] <= hi[i])) return fail("child box not inside parent box");
+                }
+                if (!walk(ref, depth + 1, n_records)) return false;
+            } else {
+                int32_t v = ~ref;
+                int first = v >> 4, count = v & 15;
+                if (count > BvhBuilder::kMaxLeaf && count != 0) return fail("leaf larger than the maximum");
+                if (first < 0 || first + count > (int)fs.records.size()) return fail("leaf range out of bounds");
+                for (int i = 0; i < count; ++i) {
+                    const Record& r = fs.records[(size_t)(first + i)];
+                    if (rec_seen[(size_t)(first + i)]++) return fail("record reachable twice");
+                    n_records++;
+                    Aabb b;
+                    if (record_box(r, b)) {
+                        if (!inside(lo, hi, b)) return fail("record not inside its leaf box");
+                    } else if (r.type == REC_INSTANCE) {
+                        if (r.c < 0 || r.c + r.b > (int)fs.xforms.size()) return fail("instance chain out of range");
+                        int sub = 0;
+                        if (!walk(r.a, depth + 1, sub)) return false;
+                    } else if (r.type == REC_MEDIUM) {
+                        if (r.a < 0 || r.a >= (int)fs.textures.size()) return fail("medium texture out of range");
+                        int sub = 0;
+                        if (r.c >= 0 && !walk(r.c, depth + 1, sub)) return false;  // -1: analytic sphere boundary
+                    } else {
+                        return fail("unknown record type");
+                    }
+                }
+            }
+        }
+        return true;
+    }
+};
+}  // namespace
+
+bool check_flat_scene(const FlatScene& fs, std::string& err) {
+    Checker c{fs, err, std::vector<int>(fs.nodes.size(), 0), std::vector<int>(fs.records.size(), 0)};
+    int n = 0;
+    if (!c.walk(fs.world_root, 0, n)) return false;
+    for (size_t i = 0; i < fs.records.size(); ++i)
+        if (c.rec_seen[i] != 1) { err = "record not reachable from the world root"; return false; }
+    for (size_t i = 0; i < fs.nodes.size(); ++i)
+        if (c.node_seen[i] != 1) { err = "node not reachable from the world root"; return false; }
+    return true;
+}
+
+}  // namespace rtx

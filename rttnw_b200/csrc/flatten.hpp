@@ -1,0 +1,46 @@
+// flatten.hpp — host side: rtx_scene_desc (the reference's object tree as data) ->
+// flat device arrays + BVHs. Replaces the pointer-chasing tree walk of
+// hittable.rs (List::hit :153-163, BvhTree :260-373) with a layout built for
+// coalesced 16-byte loads; the *results* of hit() are the contract, not the
+// reference's tree topology.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/rttnw_b200.h"
+#include "device_types.h"
+
+namespace rtx {
+
+struct Aabb {
+    double lo[3], hi[3];
+    void reset();
+    void grow(const Aabb& o);
+    void grow_point(const double p[3]);
+    double half_area() const;
+};
+
+struct FlatScene {
+    std::vector<BvhNode> nodes;
+    std::vector<Record> records;
+    std::vector<XformOp> xforms;
+    std::vector<DMaterial> materials;
+    std::vector<DTexture> textures;
+    std::vector<DPerlin> perlins;
+    int32_t world_root = 0;
+    int32_t n_media = 0;
+    int32_t n_prims = 0;  // number of primitive ids handed out
+    Aabb world_bounds;
+    CameraView camera;
+};
+
+// Returns false and fills `err` on malformed input.
+bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err);
+
+// Structural invariants of the result (every record inside every ancestor box, every
+// record reachable exactly once per BVH, leaf sizes). Host logic test hook.
+bool check_flat_scene(const FlatScene& fs, std::string& err);
+
+void camera_view(const rtx_camera& cam, const double background[3], CameraView& out);
+
+}  // namespace rtx

@@ -1,0 +1,812 @@
+// kernels.cuh — device code of the rttnw hot path for sm_100a.
+//
+//   K1 trace_rays_kernel : every Hittable::hit + Bound::hit of src/math/hittable.rs / bound.rs
+//   K2 render_kernel     : render()'s pixel loop + color() + Material::scatter/emitted +
+//                          Texture::value (src/main.rs:26-45,202-217, material.rs, texture.rs, noise.rs)
+//   K3 tonemap_kernel    : mean / sqrt / clamp / quantise (src/main.rs:217-225)
+//      reduce_tonemap_peers_kernel : K3 fused with the multi-GPU sum over NVLink peer pointers
+//
+// The reference recurses through trait objects in f64. Here: an iterative while-while BVH
+// traversal (fp32 conservative slab tests on 64-byte nodes, exact-form f64 primitive tests on
+// 96-byte records), instances entered by switching the ray's space inside the same loop,
+// hit records finalised once per query (including the Translate/YRotate post-processing of
+// hittable.rs:606-613,699-712 exactly as written, Q13/Q14), an iterative path loop with
+// per-lane path regeneration, and Philox4x32-10 counters for every random draw.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/rttnw_b200.h"
+#include "device_types.h"
+
+namespace rtx {
+
+// ---------------------------------------------------------------------------
+// small vector helpers
+// ---------------------------------------------------------------------------
+struct d3 {
+    double x, y, z;
+};
+__device__ __forceinline__ d3 mk(double x, double y, double z) { return d3{x, y, z}; }
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ d3 operator*(double s, d3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ d3 operator-(d3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double comp(d3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct RayD {
+    d3 o, d;
+    double time;
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (counter based; replaces rand::thread_rng()).
+// counter = (pixel, sample, bounce << 8 | purpose, block), key = seed.
+// ---------------------------------------------------------------------------
+enum Purpose : uint32_t { P_CAMERA = 0, P_LENS = 1, P_SCATTER = 2, P_MEDIUM = 3 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01f(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ double u01d(uint32_t w) { return (double)(w >> 8) * (1.0 / 16777216.0); }
+
+struct Sampler {
+    uint32_t k0, k1, pixel, sample, bounce;
+    __device__ __forceinline__ uint4 block(Purpose p, uint32_t j) const {
+        return philox4x32_10(pixel, sample, (bounce << 8) | (uint32_t)p, j, k0, k1);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Work counters (rtx_trace_rays_stats)
+// ---------------------------------------------------------------------------
+struct Counters {
+    unsigned long long box_tests, node_visits, sphere_tests, rect_tests, instance_enters, medium_tests;
+};
+template <bool kCount>
+struct Tally {
+    __device__ __forceinline__ void node() {}
+    __device__ __forceinline__ void sphere() {}
+    __device__ __forceinline__ void rect() {}
+    __device__ __forceinline__ void instance() {}
+    __device__ __forceinline__ void medium() {}
+};
+template <>
+struct Tally<true> {
+    uint32_t n_node = 0, n_sphere = 0, n_rect = 0, n_inst = 0, n_med = 0;
+    __device__ __forceinline__ void node() { ++n_node; }
+    __device__ __forceinline__ void sphere() { ++n_sphere; }
+    __device__ __forceinline__ void rect() { ++n_rect; }
+    __device__ __forceinline__ void instance() { ++n_inst; }
+    __device__ __forceinline__ void medium() { ++n_med; }
+};
+
+// ---------------------------------------------------------------------------
+// The ray expressed in the space currently being traversed: f64 for the primitive
+// tests, fp32 directed-rounding slab parameters for the BVH boxes.
+// ---------------------------------------------------------------------------
+struct Space {
+    d3 o, d;        // f64 origin / direction in this space
+    d3 inv_d;       // 1 / d (f64), for the rectangle plane distance
+    double inv_a;   // 1 / dot(d, d), for the sphere roots
+    float idx, idy, idz;     // fp32 1/d, magnitude clamped to 2^100
+    float anx, any, anz;     // near offsets: round-down of -o * idx
+    float afx, afy, afz;     // far offsets:  round-up   of -o * idx
+    bool sx, sy, sz;         // direction component negative: near plane is the box's hi
+};
+
+__device__ __forceinline__ float clamp_inv(float d) {
+    float inv = 1.0f / d;
+    if (!(fabsf(inv) <= 0x1p100f)) inv = copysignf(0x1p100f, d);
+    return inv;
+}
+__device__ __forceinline__ void make_space(d3 o, d3 d, Space& s) {
+    s.o = o;
+    s.d = d;
+    s.inv_d = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    s.inv_a = 1.0 / dot(d, d);
+    s.idx = clamp_inv((float)d.x);
+    s.idy = clamp_inv((float)d.y);
+    s.idz = clamp_inv((float)d.z);
+    double ax = -o.x * (double)s.idx, ay = -o.y * (double)s.idy, az = -o.z * (double)s.idz;
+    s.anx = __double2float_rd(ax); s.afx = __double2float_ru(ax);
+    s.any = __double2float_rd(ay); s.afy = __double2float_ru(ay);
+    s.anz = __double2float_rd(az); s.afz = __double2float_ru(az);
+    s.sx = s.idx < 0.0f;
+    s.sy = s.idy < 0.0f;
+    s.sz = s.idz < 0.0f;
+}
+
+// Conservative fp32 version of Bound::hit (bound.rs:13-32): never rejects a box the f64
+// test would accept. lo/hi are rounded outward at build time, the offsets are rounded
+// outward per ray, and the interval is widened by 2^-21 relative for the fma / reciprocal
+// roundings. Returns the (widened) entry distance through `tnear`.
+__device__ __forceinline__ bool slab(const Space& s, float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                     float tmin, float tmax, float& tnear) {
+    float nx = fmaf(s.sx ? hix : lox, s.idx, s.anx), fx = fmaf(s.sx ? lox : hix, s.idx, s.afx);
+    float ny = fmaf(s.sy ? hiy : loy, s.idy, s.any), fy = fmaf(s.sy ? loy : hiy, s.idy, s.afy);
+    float nz = fmaf(s.sz ? hiz : loz, s.idz, s.anz), fz = fmaf(s.sz ? loz : hiz, s.idz, s.afz);
+    float tn = fmaxf(fmaxf(nx, ny), nz);
+    float tf = fminf(fminf(fx, fy), fz);
+    tn = fmaf(-fabsf(tn), 0x1p-21f, tn);
+    tf = fmaf(fabsf(tf), 0x1p-21f, tf);
+    tnear = tn;
+    return fmaxf(tn, tmin) <= fminf(tf, tmax);
+}
+
+__device__ __forceinline__ void apply_op(const XformOp& op, d3& o, d3& d) {
+    if (op.kind == XF_TRANSLATE) {  // Translate::hit, hittable.rs:600-604
+        o = mk(o.x - op.v[0], o.y - op.v[1], o.z - op.v[2]);
+    } else {  // YRotate::hit, hittable.rs:687-692
+        double sn = op.v[0], cs = op.v[1];
+        o = mk(cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z);
+        d = mk(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Primitive tests: same operations, in the same order, as the reference (f64).
+// They only decide and return t; the hit record is built once, for the winner.
+// ---------------------------------------------------------------------------
+// Sphere::hit / MovingSphere::hit quadratic, hittable.rs:88-108,196-216 (Q9: both ends inclusive)
+__device__ __forceinline__ bool sphere_roots(const Space& s, d3 c, double r, double tmin, double tmax, double& t) {
+    d3 oc = s.o - c;
+    double half_b = dot(oc, s.d);
+    double cc = dot(oc, oc) - r * r;
+    double a = dot(s.d, s.d);
+    double disc = half_b * half_b - a * cc;
+    if (disc < 0.0) return false;
+    double sq = sqrt(disc);
+    double root = (-half_b - sq) * s.inv_a;
+    if (root < tmin || tmax < root) {
+        root = (-half_b + sq) * s.inv_a;
+        if (root < tmin || tmax < root) return false;
+    }
+    t = root;
+    return true;
+}
+__device__ __forceinline__ d3 msphere_center(const double* d, double time) {  // hittable.rs:187-191
+    double f = (time - d[7]) * d[8];
+    return mk(d[0] + f * d[3], d[1] + f * d[4], d[2] + f * d[5]);
+}
+// Rectangle::hit, hittable.rs:503-513 (Q11: t inclusive, ranges half-open, NaN never contained)
+__device__ __forceinline__ bool rect_hit(const Space& s, int plane, const double* d, double tmin, double tmax, double& t) {
+    int a0 = plane == 2 ? 1 : 0, a1 = plane == 0 ? 1 : 2, ak = plane == 0 ? 2 : (plane == 1 ? 1 : 0);
+    double tt = (d[4] - comp(s.o, ak)) * comp(s.inv_d, ak);
+    if (tt < tmin || tt > tmax) return false;
+    double p0 = comp(s.o, a0) + tt * comp(s.d, a0);
+    double p1 = comp(s.o, a1) + tt * comp(s.d, a1);
+    if (!(d[0] <= p0 && p0 < d[1]) || !(d[2] <= p1 && p1 < d[3])) return false;
+    t = tt;
+    return true;
+}
+
+struct Best {
+    double t;       // closest accepted distance so far (the `closest` of List::hit, hittable.rs:155)
+    int32_t rec;    // record index, -1 = none
+    int32_t chain;  // transform chain of the instance the record was hit in: begin | len << 24
+};
+
+constexpr int kStackSize = 48;
+constexpr int32_t kSentinel = (int32_t)0x80000000;       // bottom of a query's stack
+constexpr int32_t kLeaveInstance = (int32_t)0x80000001;  // pop: return to the query's own space
+
+__device__ __forceinline__ double ldg_d(const double* p) { return __ldg(p); }
+
+// Closest hit over the BVH rooted at `root` for `ray` in [tmin, best.t].
+// kMedia: ConstantMedium records are evaluated (world query); otherwise they cannot occur
+// (boundary queries). `stack` is a per-thread array, `sp` the first free slot.
+template <bool kMedia, bool kPrecise, bool kCount>
+__device__ __forceinline__ void traverse(const SceneView& sc, int32_t root, const RayD& ray, double tmin, Best& best,
+                                         int32_t* stack, int sp, double medium_xi, const Sampler* smp, Tally<kCount>& tally) {
+    Space s;
+    make_space(ray.o, ray.d, s);
+    float tmin_f = __double2float_rd(tmin);
+    float tmax_f = __double2float_ru(best.t);
+    int32_t cur_chain = 0;
+    const int sp0 = sp;
+    stack[sp++] = kSentinel;
+    int32_t cur = root;
+    while (true) {
+        // ---- inner nodes ----
+        while (cur >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            int4 meta = __ldg(reinterpret_cast<const int4*>(np + 3));
+            tally.node();
+            float n0, n1;
+            bool h0 = slab(s, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, tmin_f, tmax_f, n0);
+            bool h1 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, n1);
+            if (h0 && h1) {
+                bool swap = n1 < n0;
+                stack[sp++] = swap ? meta.x : meta.y;
+                cur = swap ? meta.y : meta.x;
+            } else if (h0) {
+                cur = meta.x;
+            } else if (h1) {
+                cur = meta.y;
+            } else {
+                cur = stack[--sp];
+            }
+        }
+        if (cur == kSentinel) break;
+        if (cur == kLeaveInstance) {
+            make_space(ray.o, ray.d, s);
+            cur_chain = 0;
+            cur = stack[--sp];
+            continue;
+        }
+        // ---- leaf ----
+        int32_t v = ~cur;
+        int32_t first = v >> 4, count = v & 15;
+        cur = stack[--sp];
+        for (int32_t i = 0; i < count; ++i) {
+            const Record* rp = sc.records + first + i;
+            int4 h = __ldg(reinterpret_cast<const int4*>(rp));
+            const double* d = rp->d;
+            double t;
+            bool hit = false;
+            if (h.x == REC_SPHERE) {
+                tally.sphere();
+                double2 a = __ldg(reinterpret_cast<const double2*>(d)), b = __ldg(reinterpret_cast<const double2*>(d + 2));
+                hit = sphere_roots(s, mk(a.x, a.y, b.x), b.y, tmin, best.t, t);
+            } else if (h.x == REC_MSPHERE) {
+                tally.sphere();
+                double dd[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dd[k] = ldg_d(d + k);
+                hit = sphere_roots(s, msphere_center(dd, ray.time), dd[6], tmin, best.t, t);
+            } else if (h.x <= REC_RECT_YZ) {
+                tally.rect();
+                double dd[5];
+                double2 a = __ldg(reinterpret_cast<const double2*>(d)), b = __ldg(reinterpret_cast<const double2*>(d + 2));
+                dd[0] = a.x; dd[1] = a.y; dd[2] = b.x; dd[3] = b.y; dd[4] = ldg_d(d + 4);
+                hit = rect_hit(s, h.x - REC_RECT_XY, dd, tmin, best.t, t);
+            } else if (h.x == REC_INSTANCE) {
+                // enter the instance: re-express the ray (Translate/YRotate::hit), keep traversing in the same loop
+                tally.instance();
+                d3 o = ray.o, dir = ray.d;
+                for (int32_t k = 0; k < h.z; ++k) {
+                    XformOp op = sc.xforms[h.w + k];
+                    apply_op(op, o, dir);
+                }
+                make_space(o, dir, s);
+                cur_chain = h.w | (h.z << 24);
+                stack[sp++] = cur;  // what we were about to visit next, resumed after the instance
+                stack[sp++] = kLeaveInstance;
+                cur = h.y;
+            } else if (kMedia) {  // REC_MEDIUM: ConstantMedium::hit, hittable.rs:740-796 (Q16)
+                tally.medium();
+                double r1, r2;
+                bool ok;
+                if (h.w < 0) {
+                    // boundary = one untransformed sphere: hit(-inf, inf) is the near root, hit(t1 + 1e-4, inf) the far
+                    // root if it clears t1 + 1e-4 (Sphere::hit tries the near root first; it is below the new t_min)
+                    d3 c = mk(ldg_d(d + 4), ldg_d(d + 5), ldg_d(d + 6));
+                    double rad = ldg_d(d + 7);
+                    d3 oc = ray.o - c;
+                    double a = dot(ray.d, ray.d), half_b = dot(oc, ray.d), cc = dot(oc, oc) - rad * rad;
+                    double disc = half_b * half_b - a * cc;
+                    ok = !(disc < 0.0);
+                    double sq = sqrt(disc);
+                    double inv_a = 1.0 / a;
+                    r1 = (-half_b - sq) * inv_a;
+                    r2 = (-half_b + sq) * inv_a;
+                    ok = ok && !(r2 < r1 + 0.0001);
+                } else {
+                    Best b1{CUDART_INF, -1, 0};
+                    traverse<false, kPrecise, kCount>(sc, h.w, ray, -CUDART_INF, b1, stack, sp, 0.0, nullptr, tally);
+                    ok = b1.rec >= 0;
+                    r1 = b1.t;
+                    if (ok) {
+                        Best b2{CUDART_INF, -1, 0};
+                        traverse<false, kPrecise, kCount>(sc, h.w, ray, r1 + 0.0001, b2, stack, sp, 0.0, nullptr, tally);
+                        ok = b2.rec >= 0;
+                        r2 = b2.t;
+                    }
+                }
+                if (ok) {
+                    r1 = fmax(r1, tmin);
+                    r2 = fmin(r2, best.t);
+                    if (r1 < r2) {
+                        r1 = fmax(r1, 0.0);
+                        double len = sqrt(dot(ray.d, ray.d));
+                        double inside = (r2 - r1) * len;
+                        int32_t ord = (int32_t)ldg_d(d + 1);
+                        double hit_distance;
+                        if (smp) {
+                            uint4 w = smp->block(P_MEDIUM, (uint32_t)ord >> 2);
+                            uint32_t word = (ord & 3) == 0 ? w.x : ((ord & 3) == 1 ? w.y : ((ord & 3) == 2 ? w.z : w.w));
+                            hit_distance = kPrecise ? ldg_d(d) * log(u01d(word)) : ldg_d(d) * (double)logf(u01f(word));
+                        } else {
+                            hit_distance = ldg_d(d) * log(medium_xi);
+                        }
+                        if (!(hit_distance > inside)) {
+                            t = r1 + hit_distance / len;
+                            hit = true;
+                        }
+                    }
+                }
+            }
+            if (hit) {
+                best.t = t;
+                best.rec = first + i;
+                best.chain = (h.x == REC_MEDIUM) ? 0 : cur_chain;
+                tmax_f = __double2float_ru(t);
+            }
+        }
+    }
+    (void)sp0;
+}
+
+// ---------------------------------------------------------------------------
+// Hit record of the winning record (HitRecord, hittable.rs:15-27), built once.
+// ---------------------------------------------------------------------------
+struct HitOut {
+    d3 p, n;       // point and (face-flipped, possibly Q14-mangled) normal
+    d3 on;         // outward unit normal in object space (spheres: the argument of Sphere::uv)
+    double u, v;   // rectangles always; spheres when kPrecise
+    int32_t material;  // material index, or -(1 + texture) for a medium's Isotropic
+    int32_t prim_id;
+    int32_t type;
+    bool front_face;
+};
+
+__device__ __forceinline__ void sphere_uv(d3 p, double& u, double& v) {  // hittable.rs:77-83
+    const double PI = 3.14159265358979323846;
+    double theta = acos(-p.y);
+    double phi = atan2(-p.z, p.x) + PI;
+    u = phi / (2.0 * PI);
+    v = theta / PI;
+}
+
+template <bool kPrecise>
+__device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ray, const Best& best, HitOut& out) {
+    const Record* rp = sc.records + best.rec;
+    int4 h = __ldg(reinterpret_cast<const int4*>(rp));
+    const double* d = rp->d;
+    int32_t begin = best.chain & 0xFFFFFF, len = (uint32_t)best.chain >> 24;
+    if (h.x == REC_MEDIUM) {
+        begin = (int32_t)ldg_d(d + 2);
+        len = (int32_t)ldg_d(d + 3);
+    }
+    d3 o = ray.o, dir = ray.d;
+    for (int32_t k = 0; k < len; ++k) apply_op(sc.xforms[begin + k], o, dir);
+    double t = best.t;
+    d3 p = o + t * dir;  // Ray::point_at_parameter in the primitive's own space
+    d3 n;
+    bool ff;
+    out.u = 0.0;
+    out.v = 0.0;
+    out.type = h.x;
+    out.prim_id = h.z;
+    out.material = h.y;
+    if (h.x == REC_MEDIUM) {  // hittable.rs:778-789: arbitrary normal, front_face = true, u = v = 0
+        n = mk(1.0, 0.0, 0.0);
+        ff = true;
+        out.on = n;
+        out.material = -(1 + h.y);
+    } else {
+        d3 outward;
+        if (h.x == REC_SPHERE) {
+            d3 c = mk(ldg_d(d), ldg_d(d + 1), ldg_d(d + 2));
+            double r = ldg_d(d + 3);
+            outward = mk((p.x - c.x) / r, (p.y - c.y) / r, (p.z - c.z) / r);  // hittable.rs:111
+            if (kPrecise) sphere_uv(outward, out.u, out.v);
+        } else if (h.x == REC_MSPHERE) {
+            double dd[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) dd[k] = ldg_d(d + k);
+            d3 c = msphere_center(dd, ray.time);
+            outward = mk((p.x - c.x) / dd[6], (p.y - c.y) / dd[6], (p.z - c.z) / dd[6]);  // hittable.rs:219; u = v = 0 (Q10)
+        } else {
+            int plane = h.x - REC_RECT_XY;
+            int a0 = plane == 2 ? 1 : 0, a1 = plane == 0 ? 1 : 2;
+            double r0 = ldg_d(d), r1 = ldg_d(d + 1), r2 = ldg_d(d + 2), r3 = ldg_d(d + 3);
+            double p0 = comp(o, a0) + t * comp(dir, a0), p1 = comp(o, a1) + t * comp(dir, a1);
+            out.u = (p0 - r0) / (r1 - r0);  // hittable.rs:515-516
+            out.v = (p1 - r2) / (r3 - r2);
+            outward = mk(plane == 2 ? 1.0 : 0.0, plane == 1 ? 1.0 : 0.0, plane == 0 ? 1.0 : 0.0);  // +k axis (Q11)
+        }
+        out.on = outward;
+        ff = dot(dir, outward) < 0.0;  // HitRecord::face_normal, hittable.rs:30-44
+        n = ff ? outward : -outward;
+    }
+    // unwind the wrappers, innermost first (what Translate::hit / YRotate::hit do on the way out)
+    for (int32_t k = len - 1; k >= 0; --k) {
+        XformOp op = sc.xforms[begin + k];
+        if (op.kind == XF_ROTATE_Y) {
+            double sn = op.v[0], cs = op.v[1];
+            // Q14 (hittable.rs:700-705): [0] is overwritten first and the NEW [0] feeds [2]
+            p.x = cs * p.x + sn * p.z;
+            p.z = -sn * p.x + cs * p.z;
+            n.x = cs * n.x + sn * n.z;
+            n.z = -sn * n.x + cs * n.z;
+            ff = dot(dir, n) < 0.0;  // against the object-space ray (hittable.rs:706)
+            n = ff ? n : -n;
+            dir = mk(cs * dir.x + sn * dir.z, dir.y, -sn * dir.x + cs * dir.z);  // direction one level out
+        } else {
+            ff = dot(dir, n) < 0.0;  // Q13 (hittable.rs:607): face_normal re-run on the flipped normal
+            n = ff ? n : -n;
+            p = mk(p.x + op.v[0], p.y + op.v[1], p.z + op.v[2]);
+        }
+    }
+    out.p = p;
+    out.n = n;
+    out.front_face = ff;
+}
+
+// ---------------------------------------------------------------------------
+// K1: fixed rays
+// ---------------------------------------------------------------------------
+template <bool kCount>
+__global__ void __launch_bounds__(128) trace_rays_kernel(SceneView sc, int64_t n, const rtx_ray* __restrict__ rays,
+                                                         rtx_hit* __restrict__ hits, Counters* counters) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Tally<kCount> tally;
+    int32_t stack[kStackSize];
+    if (i < n) {
+        const double2* rp = reinterpret_cast<const double2*>(rays + i);  // 80 bytes = 5 x 16
+        double2 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2), d = __ldg(rp + 3), e = __ldg(rp + 4);
+        RayD ray{mk(a.x, a.y, b.x), mk(b.y, c.x, c.y), d.x};
+        double tmin = d.y, tmax = e.x, xi = e.y;
+        Best best{tmax, -1, 0};
+        traverse<true, true, kCount>(sc, sc.world_root, ray, tmin, best, stack, 0, xi, nullptr, tally);
+        if (!kCount) {
+            rtx_hit h;
+            if (best.rec >= 0) {
+                HitOut ho;
+                finalize_hit<true>(sc, ray, best, ho);
+                h.prim_id = ho.prim_id; h.material = ho.material; h.front_face = ho.front_face ? 1 : 0; h._pad = 0;
+                h.t = best.t;
+                h.p[0] = ho.p.x; h.p[1] = ho.p.y; h.p[2] = ho.p.z;
+                h.normal[0] = ho.n.x; h.normal[1] = ho.n.y; h.normal[2] = ho.n.z;
+                h.u = ho.u; h.v = ho.v;
+            } else {
+                h.prim_id = RTX_MISS; h.material = -1; h.front_face = 0; h._pad = 0;
+                h.t = 0; h.p[0] = h.p[1] = h.p[2] = 0; h.normal[0] = h.normal[1] = h.normal[2] = 0; h.u = h.v = 0;
+            }
+            hits[i] = h;
+        }
+    }
+    if constexpr (kCount) {
+        // warp-reduce, one atomic per warp per counter
+        uint32_t vals[5] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst, tally.n_med};
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], off);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
+            atomicAdd(&counters->box_tests, 2ull * vals[0]);
+            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
+            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
+            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
+            atomicAdd(&counters->medium_tests, (unsigned long long)vals[4]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Textures (src/math/texture.rs, noise.rs), fp32
+// ---------------------------------------------------------------------------
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 mkf(float x, float y, float z) { return f3{x, y, z}; }
+
+__device__ __forceinline__ float perlin_noise(const DPerlin* __restrict__ tab, float px, float py, float pz) {  // noise.rs:49-94
+    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    float u = px - fx, v = py - fy, w = pz - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.f - 2.f * u), vv = v * v * (3.f - 2.f * v), ww = w * w * (3.f - 2.f * w);
+    float acc = 0.f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di) {
+        uint32_t hx = tab->perm[0][(i + di) & 255];
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj) {
+            uint32_t hy = tab->perm[1][(j + dj) & 255];
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                uint32_t hz = tab->perm[2][(k + dk) & 255];
+                float4 g = __ldg(reinterpret_cast<const float4*>(tab->ranvec[hx ^ hy ^ hz]));
+                float wu = di ? uu : 1.f - uu, wv = dj ? vv : 1.f - vv, wwt = dk ? ww : 1.f - ww;
+                acc += wu * wv * wwt * (g.x * (u - di) + g.y * (v - dj) + g.z * (w - dk));
+            }
+        }
+    }
+    return acc;
+}
+__device__ __forceinline__ float perlin_turbulence(const DPerlin* tab, float px, float py, float pz) {  // noise.rs:96-108, depth 7
+    float acc = 0.f, weight = 1.f;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) {
+        acc += weight * perlin_noise(tab, px, py, pz);
+        weight *= 0.5f;
+        px *= 2.f; py *= 2.f; pz *= 2.f;
+    }
+    return acc;
+}
+
+// Texture::value. (u, v) are only meaningful when the texture's uses-uv flag is set.
+__device__ __forceinline__ f3 texture_value(const SceneView& sc, int32_t ti, float u, float v, d3 p) {
+    DTexture t = sc.textures[ti];
+    // CheckerTexture (texture.rs:15-30, Q21) selects a child; children may nest
+    for (int guard = 0; guard < 8 && t.kind == RTX_TEX_CHECKER; ++guard) {
+        // f64 products keep the stripe edges of the radius-1000 ground sphere where the reference puts them
+        float sines = sinf((float)(10.0 * p.x)) * sinf((float)(10.0 * p.y)) * sinf((float)(10.0 * p.z));
+        t = sc.textures[sines < 0.f ? t.a : t.b];
+    }
+    if (t.kind == RTX_TEX_SOLID) return mkf(t.f[0], t.f[1], t.f[2]);
+    if (t.kind == RTX_TEX_NOISE) {  // texture.rs:52-59 (Q22)
+        float turb = perlin_turbulence(sc.perlins + t.a, (float)p.x, (float)p.y, (float)p.z);
+        float g = 0.5f * (1.f + sinf(t.f[0] * (float)p.z + 10.f * turb));
+        return mkf(g, g, g);
+    }
+    if (t.kind == RTX_TEX_IMAGE) {  // texture.rs:77-106 (Q23): nearest texel, bytes / 255
+        DImage img = sc.images[t.a];
+        if (img.tex == 0) return mkf(0.f, 1.f, 1.f);
+        float uu = fminf(fmaxf(u, 0.f), 1.f), vv = 1.f - fminf(fmaxf(v, 0.f), 1.f);
+        int i = (int)(uu * (float)img.width), j = (int)(vv * (float)img.height);
+        i = min(i, img.width - 1);
+        j = min(j, img.height - 1);
+        uchar4 px = tex2D<uchar4>((cudaTextureObject_t)img.tex, (float)i + 0.5f, (float)j + 0.5f);
+        const float s = 1.0f / 255.0f;
+        return mkf(px.x * s, px.y * s, px.z * s);
+    }
+    return mkf(0.f, 0.f, 0.f);
+}
+
+// Vec3f::random_in_unit_space, vec3.rs:149-160: candidate j = Philox block (SCATTER, j) words 0..2.
+// The candidates are exact in fp32 and their squared length is exact in f64, so the accept /
+// reject decisions are identical to the oracle's. `w3_first` returns word 3 of block 0
+// (the Dielectric's uniform, material.rs:189).
+__device__ __forceinline__ d3 random_in_unit_space(const Sampler& smp) {
+    for (uint32_t j = 0;; ++j) {
+        uint4 w = smp.block(P_SCATTER, j);
+        double x = 2.0 * u01d(w.x) - 1.0, y = 2.0 * u01d(w.y) - 1.0, z = 2.0 * u01d(w.z) - 1.0;
+        if (x * x + y * y + z * z < 1.0) return mk(x, y, z);
+    }
+}
+
+struct RenderArgs {
+    SceneView sc;
+    CameraView cam;
+    int32_t width, height, spp_begin, spp_count, max_depth;
+    uint32_t k0, k1;
+    int32_t tiles_x, tiles_y;
+};
+
+constexpr int kTileW = 8, kTileH = 4;  // one warp = one 8x4 pixel tile
+
+// ---------------------------------------------------------------------------
+// K2: the path loop. One warp owns one tile at a time (dynamic fetch); each lane owns one
+// pixel and runs its samples back to back, starting its next path as soon as the current
+// one ends, so lanes at different bounce depths still execute the same traversal code.
+// ---------------------------------------------------------------------------
+template <bool kCount>
+__global__ void __launch_bounds__(128) render_kernel(RenderArgs a, float4* __restrict__ accum, unsigned long long* ray_count,
+                                                     unsigned int* work_counter, Counters* counters) {
+    const int lane = threadIdx.x & 31;
+    int32_t stack[kStackSize];
+    Tally<kCount> tally;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    unsigned long long my_rays = 0;
+    while (true) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(work_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= (unsigned int)n_tiles) break;
+        int tx = (int)(tile % (unsigned int)a.tiles_x), ty = (int)(tile / (unsigned int)a.tiles_x);
+        int px = tx * kTileW + (lane & (kTileW - 1)), row = ty * kTileH + (lane / kTileW);  // row 0 = top
+        bool active = px < a.width && row < a.height;
+        int jrow = a.height - 1 - row;  // main.rs:202-204: j runs height-1 .. 0, top row first
+        Sampler smp{a.k0, a.k1, (uint32_t)(row * a.width + px), 0u, 0u};
+        float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f;
+        int s_idx = 0;
+        bool need_new = true;
+        RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
+        float thr_r = 1.f, thr_g = 1.f, thr_b = 1.f, rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
+        int bounce = 0;
+        bool done = !active;
+        while (!__all_sync(0xffffffffu, done)) {
+            if (done) continue;
+            if (need_new) {
+                if (s_idx >= a.spp_count) {
+                    done = true;
+                    continue;
+                }
+                // one path sample: pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25)
+                smp.sample = (uint32_t)(a.spp_begin + s_idx);
+                smp.bounce = 0;
+                uint4 w = smp.block(P_CAMERA, 0);
+                double su = ((double)px + u01d(w.x)) / (double)a.width;
+                double sv = ((double)jrow + u01d(w.y)) / (double)a.height;
+                double lx = 0.0, ly = 0.0;
+                if (a.cam.lens_radius != 0.0) {  // the draw is skipped for a pinhole: counters make that invisible
+                    for (uint32_t j = 0;; ++j) {
+                        uint4 l = smp.block(P_LENS, j);
+                        lx = 2.0 * u01d(l.x) - 1.0; ly = 2.0 * u01d(l.y) - 1.0;
+                        if (lx * lx + ly * ly < 1.0) break;
+                        lx = 2.0 * u01d(l.z) - 1.0; ly = 2.0 * u01d(l.w) - 1.0;
+                        if (lx * lx + ly * ly < 1.0) break;
+                    }
+                }
+                double rdx = a.cam.lens_radius * lx, rdy = a.cam.lens_radius * ly;
+                d3 off = mk(a.cam.u[0] * rdx + a.cam.v[0] * rdy, a.cam.u[1] * rdx + a.cam.v[1] * rdy, a.cam.u[2] * rdx + a.cam.v[2] * rdy);
+                ray.o = mk(a.cam.origin[0] + off.x, a.cam.origin[1] + off.y, a.cam.origin[2] + off.z);
+                ray.d = mk(a.cam.lower_left[0] + su * a.cam.horizontal[0] + sv * a.cam.vertical[0] - a.cam.origin[0] - off.x,
+                           a.cam.lower_left[1] + su * a.cam.horizontal[1] + sv * a.cam.vertical[1] - a.cam.origin[1] - off.y,
+                           a.cam.lower_left[2] + su * a.cam.horizontal[2] + sv * a.cam.vertical[2] - a.cam.origin[2] - off.z);
+                ray.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01d(w.z);
+                thr_r = thr_g = thr_b = 1.f;
+                rad_r = rad_g = rad_b = 0.f;
+                bounce = 0;
+                need_new = false;
+            }
+            // ---- color(), main.rs:26-45, one level per iteration (Q7) ----
+            smp.bounce = (uint32_t)bounce;
+            Best best{1.7976931348623157e308, -1, 0};
+            traverse<true, false, kCount>(a.sc, a.sc.world_root, ray, 0.001, best, stack, 0, 0.0, &smp, tally);
+            ++my_rays;
+            bool end_path = false;
+            if (best.rec < 0) {  // background (Q8)
+                rad_r += thr_r * a.cam.background[0]; rad_g += thr_g * a.cam.background[1]; rad_b += thr_b * a.cam.background[2];
+                end_path = true;
+            } else {
+                HitOut ho;
+                finalize_hit<false>(a.sc, ray, best, ho);
+                int32_t mkind, mtex;
+                float alb_r = 0.f, alb_g = 0.f, alb_b = 0.f, mparam = 0.f;
+                if (ho.material < 0) {  // ConstantMedium's own Isotropic (hittable.rs:726,786)
+                    mkind = RTX_MAT_ISOTROPIC;
+                    mtex = -(ho.material + 1);
+                } else {
+                    DMaterial m = a.sc.materials[ho.material];
+                    mkind = m.kind; mtex = m.texture; alb_r = m.albedo[0]; alb_g = m.albedo[1]; alb_b = m.albedo[2]; mparam = m.param;
+                }
+                float tu = (float)ho.u, tv = (float)ho.v;
+                if (mtex >= 0 && ho.type == REC_SPHERE && a.sc.textures[mtex]._pad) {
+                    // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
+                    const float PI = 3.14159265358979f;
+                    tv = acosf(-(float)ho.on.y) / PI;
+                    tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+                }
+                d3 udir;
+                if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
+                    f3 e = texture_value(a.sc, mtex, tu, tv, ho.p);
+                    rad_r += thr_r * e.x; rad_g += thr_g * e.y; rad_b += thr_b * e.z;
+                    end_path = true;
+                } else if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
+                    d3 b = random_in_unit_space(smp);
+                    ray.d = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
+                    f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
+                    thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
+                } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
+                    ray.d = random_in_unit_space(smp);
+                    f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
+                    thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
+                } else if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
+                    double k = 1.0 / sqrt(dot(ray.d, ray.d));
+                    udir = k * ray.d;
+                    d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
+                    d3 b = random_in_unit_space(smp);
+                    d3 nd = refl + (double)mparam * b;
+                    if (dot(nd, ho.n) > 0.0) {
+                        ray.d = nd;
+                        thr_r *= alb_r; thr_g *= alb_g; thr_b *= alb_b;
+                    } else {
+                        end_path = true;  // absorbed: only `emitted` (= 0) is returned
+                    }
+                } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
+                    double ir = (double)mparam;
+                    double ratio = ho.front_face ? 1.0 / ir : ir;
+                    double k = 1.0 / sqrt(dot(ray.d, ray.d));
+                    udir = k * ray.d;
+                    double cos_theta = fmin(dot(-udir, ho.n), 1.0);
+                    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+                    bool reflect = ratio * sin_theta > 1.0;
+                    if (!reflect) {
+                        double r0 = (1.0 - ratio) / (1.0 + ratio);
+                        r0 = r0 * r0;
+                        double om = 1.0 - cos_theta;
+                        double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
+                        uint4 w = smp.block(P_SCATTER, 0);
+                        reflect = schlick > u01d(w.w);
+                    }
+                    if (reflect) {
+                        ray.d = udir - (2.0 * dot(udir, ho.n)) * ho.n;
+                    } else {  // vec3.rs:116-121
+                        d3 perp = ratio * (udir + cos_theta * ho.n);
+                        d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
+                        ray.d = perp + par;
+                    }
+                }
+                ray.o = ho.p;
+                ++bounce;
+                if (bounce >= a.max_depth) end_path = true;  // color(depth = 0) returns 0
+            }
+            if (end_path) {
+                sum_r += rad_r; sum_g += rad_g; sum_b += rad_b;
+                ++s_idx;
+                need_new = true;
+            }
+        }
+        if (active) {
+            float* dst = reinterpret_cast<float*>(accum + (size_t)row * a.width + px);
+            atomicAdd(dst + 0, sum_r);
+            atomicAdd(dst + 1, sum_g);
+            atomicAdd(dst + 2, sum_b);
+            atomicAdd(dst + 3, (float)a.spp_count);
+        }
+    }
+    if (ray_count) {
+        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, off);
+        if (lane == 0 && my_rays) atomicAdd(ray_count, my_rays);
+    }
+    if constexpr (kCount) {
+        uint32_t vals[5] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst, tally.n_med};
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], off);
+        if (lane == 0) {
+            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
+            atomicAdd(&counters->box_tests, 2ull * vals[0]);
+            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
+            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
+            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
+            atomicAdd(&counters->medium_tests, (unsigned long long)vals[4]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: main.rs:217-225 (Q26). NaN -> 0 like Rust's `as u8`.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t quantise(float sum, float inv_n) {
+    float x = sqrtf(sum * inv_n);
+    x = fminf(fmaxf(x, 0.f), 0.999f) * 256.f;  // fmaxf/fminf drop NaN -> 0
+    return (uint8_t)(int)x;
+}
+__global__ void tonemap_kernel(const float4* __restrict__ accum, int n_pixels, uchar4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float4 a = accum[i];
+    float inv = 1.0f / a.w;
+    out[i] = make_uchar4(quantise(a.x, inv), quantise(a.y, inv), quantise(a.z, inv), 255);
+}
+
+constexpr int kMaxPeers = 16;
+struct PeerList {
+    const float4* p[kMaxPeers];
+    int n;
+};
+// Rank-0 side of the multi-GPU combine: reads every peer's accumulator straight over NVLink
+// (peer-mapped pointers), adds it to the local one, writes the sum back and tonemaps — one pass.
+__global__ void reduce_tonemap_peers_kernel(float4* __restrict__ accum, PeerList peers, int n_pixels, uchar4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float4 a = accum[i];
+    for (int k = 0; k < peers.n; ++k) {
+        float4 b = peers.p[k][i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    accum[i] = a;
+    float inv = 1.0f / a.w;
+    out[i] = make_uchar4(quantise(a.x, inv), quantise(a.y, inv), quantise(a.z, inv), 255);
+}
+
+}  // namespace rtx

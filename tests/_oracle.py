@@ -35,7 +35,7 @@ def load() -> C.CDLL:
         "orc_scene_camera": (None, [_P, C.POINTER(abi.Camera), C.POINTER(C.c_double * 3)]),
         "orc_trace_rays": (None, [_P, C.c_int64, _P, _P, _P, C.c_int]),
         "orc_render": (C.c_uint64, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
-                                    C.c_int, _P, C.c_int]),
+                                    C.c_int, C.c_int, _P, C.c_int]),
         "orc_tonemap": (None, [_P, C.c_int, C.c_double, _P]),
         "orc_philox4x32_10": (None, [C.POINTER(C.c_uint32 * 4), C.POINTER(C.c_uint32 * 2), C.POINTER(C.c_uint32 * 4)]),
         "orc_sphere_uv": (None, [C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 2)]),
@@ -105,11 +105,12 @@ class OracleScene:
         return hits, fragile.astype(bool)
 
     def render_sum(self, width: int, height: int, spp: int, seed: int = 1, spp_begin: int = 0, max_depth: int = 50,
-                   rows=None, threads: int = 0):
+                   rows=None, row_stride: int = 1, threads: int = 0):
         """Returns (rgb_sum float64 (H,W,3), n_rays)."""
         out = np.zeros((height, width, 3), dtype=np.float64)
         r0, r1 = rows if rows is not None else (0, height)
-        n = self.lib.orc_render(self.h, width, height, spp_begin, spp, max_depth, seed, r0, r1, out.ctypes.data, threads)
+        n = self.lib.orc_render(self.h, width, height, spp_begin, spp, max_depth, seed, r0, r1, row_stride,
+                                out.ctypes.data, threads)
         return out, int(n)
 
     def tonemap(self, rgb_sum: np.ndarray, samples: float) -> np.ndarray:

@@ -1,0 +1,354 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Fixed rays (BASELINE.json): primitive id bit-exact outside grazing ties, t / p / normal / u / v
+within 1e-5 relative. Renders: PSNR >= 35 dB and mean per-channel error <= 1/255 at equal high
+spp, plus same-counter (Philox) low-depth comparisons that are nearly sample-exact.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import rttnw_b200 as R
+from rttnw_b200 import abi
+from rttnw_b200 import scene as S
+from tests import _oracle as O
+from tests import _rays as RY
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = R.Context(0)
+    yield c
+    c.close()
+
+
+def both(ctx, desc, bvh_seed=7):
+    return R.DeviceScene(ctx, desc), O.OracleScene.from_desc(desc, bvh_seed)
+
+
+def check_rays(gpu_scene, osc, rays, min_ok=0.98):
+    ref, fragile = osc.trace(rays)
+    got = gpu_scene.trace(rays)
+    st = RY.compare_hits(got, ref, fragile)
+    assert 1.0 - st["fragile"] / max(1, st["rays"]) >= min_ok, st
+    return got, ref, st
+
+
+# ---------------------------------------------------------------------------
+# known answers through the C ABI (same cases that pin the oracle)
+# ---------------------------------------------------------------------------
+def test_primitive_known_answers(ctx):
+    mat = S.Lambertian((0.5, 0.5, 0.5))
+    sc = R.DeviceScene(ctx, S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, mat)])).to_desc())
+    h = sc.trace(O.make_rays((0, 0, -5), (0, 0, 1)))[0]
+    assert h["prim_id"] == 0 and h["t"] == pytest.approx(4.0) and h["front_face"] == 1
+    assert tuple(h["normal"]) == pytest.approx((0, 0, -1)) and (h["u"], h["v"]) == pytest.approx((0.75, 0.5))
+    assert sc.trace(O.make_rays((0, 0, -5), (0, 0, 1), t_max=4.0))[0]["prim_id"] == 0  # inclusive t_max (Q9)
+    assert sc.trace(O.make_rays((0, 0, -5), (0, 0, 1), t_max=3.999))[0]["prim_id"] == abi.RTX_MISS
+    h = sc.trace(O.make_rays((0, 0, 0), (0, 0, 1)))[0]
+    assert h["t"] == pytest.approx(1.0) and h["front_face"] == 0
+    sc = R.DeviceScene(ctx, S.Scene(S.List([S.XY.rectangle(mat, (0, 2), (0, 4), 1.0)])).to_desc())
+    assert sc.trace(O.make_rays((0, 1, 0), (0, 0, 1)))[0]["prim_id"] == 0  # half-open ranges (Q11)
+    assert sc.trace(O.make_rays((2, 1, 0), (0, 0, 1)))[0]["prim_id"] == abi.RTX_MISS
+    assert sc.trace(O.make_rays((1, 1, 0), (1, 0, 0)))[0]["prim_id"] == abi.RTX_MISS  # parallel ray
+    h = sc.trace(O.make_rays((1, 1, 0), (0, 0, 1)))[0]
+    assert (h["u"], h["v"]) == pytest.approx((0.5, 0.25)) and h["front_face"] == 0
+    sc = R.DeviceScene(ctx, S.Scene(S.List([S.Cube((0, 0, 0), (1, 2, 3), mat)])).to_desc())
+    for d, face in {(0, 0, 1): 0, (0, 0, -1): 1, (0, 1, 0): 2, (0, -1, 0): 3, (1, 0, 0): 4, (-1, 0, 0): 5}.items():
+        o = tuple((0.5, 1.0, 1.5)[i] - 10 * d[i] for i in range(3))
+        assert sc.trace(O.make_rays(o, d))[0]["prim_id"] == face  # Cube::new order (Q12)
+
+
+def test_yrotate_quirk_and_translate(ctx):  # Q13 / Q14 closed forms
+    mat = S.Lambertian((0.5, 0.5, 0.5))
+    th = math.radians(15.0)
+    s, c = math.sin(th), math.cos(th)
+    rect = S.XY.rectangle(mat, (-5, 5), (-5, 5), 1.0)
+    sc = R.DeviceScene(ctx, S.Scene(S.List([rect.rotate_y(15.0).translate((10, 20, 30))])).to_desc())
+
+    def to_world(v):
+        return np.array([c * v[0] + s * v[2], v[1], -s * v[0] + c * v[2]])
+    o = to_world(np.array([0.3, 0.2, 5.0])) + np.array([10, 20, 30.0])
+    h = sc.trace(O.make_rays(o, to_world(np.array([0.0, 0.0, -1.0]))))[0]
+    p0 = c * 0.3 + s
+    assert h["t"] == pytest.approx(4.0)
+    assert tuple(h["normal"]) == pytest.approx((s, 0.0, -s * s + c))
+    assert tuple(h["p"]) == pytest.approx((p0 + 10, 20.2, -s * p0 + c + 30))
+
+
+def test_constant_medium_known_answer(ctx):  # Q16
+    density, xi = 0.5, 0.6
+    dist = -math.log(xi) / density
+    for boundary in (S.Sphere((0, 0, 0), 2.0, S.Dielectric(1.5)),  # analytic fast path
+                     S.Sphere((0, 0, 0), 2.0, S.Dielectric(1.5)).translate((0, 0, 0))):  # general boundary query
+        sc = R.DeviceScene(ctx, S.Scene(S.List([S.ConstantMedium(boundary, density, (1, 1, 1))])).to_desc())
+        h = sc.trace(O.make_rays((0, 0, -5), (0, 0, 2), xi=xi))[0]
+        assert h["prim_id"] == 1 and h["t"] == pytest.approx(1.5 + dist / 2.0)
+        assert tuple(h["normal"]) == (1.0, 0.0, 0.0) and h["front_face"] == 1 and h["material"] == -1
+        assert sc.trace(O.make_rays((0, 0, -5), (0, 0, 2), xi=math.exp(-density * 4.0 * 1.01)))[0]["prim_id"] == abi.RTX_MISS
+        assert sc.trace(O.make_rays((0, 0, 0), (0, 0, 1), xi=xi))[0]["t"] == pytest.approx(0.001 + dist)
+        assert sc.trace(O.make_rays((0, 0, -5), (0, 0, 2), xi=xi, t_max=1.4))[0]["prim_id"] == abi.RTX_MISS
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    mat = S.Lambertian((0.5, 0.5, 0.5))
+    sc = R.DeviceScene(ctx, S.Scene(S.List([])).to_desc())  # empty world
+    assert sc.trace(O.make_rays((0, 0, 0), (0, 0, 1)))[0]["prim_id"] == abi.RTX_MISS
+    assert sc.trace(np.zeros(0, dtype=abi.RAY_DTYPE)).shape == (0,)  # zero rays
+    sc, osc = both(ctx, S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, mat), S.XZ.rectangle(mat, (-3, 3), (-3, 3), -1.0)])).to_desc())
+    rays = O.make_rays([(0, 0, -5), (0, 0, -5), (0, 5, 0), (0, 0, -5), (1e30, 0, 0)],
+                       [(0, 0, 0), (0, 0, 1e-300), (0, -1, 0), (1, 0, 0), (-1, 0, 0)])
+    got, ref = sc.trace(rays), osc.trace(rays)[0]
+    assert np.array_equal(got["prim_id"], ref["prim_id"])  # zero / denormal / axis-aligned directions, far origins
+
+
+# ---------------------------------------------------------------------------
+# fixed rays on the nine scenes of scenes.rs
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("number", range(1, 10))
+def test_fixed_rays_builtin_scene(ctx, number, earth_rgba):
+    n = 60000 if number in (1, 9) else 100000
+    rng = np.random.default_rng(0xF17ED + number)
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(number))
+    osc = O.OracleScene.builtin(number, earth=earth_rgba)  # the oracle's OWN restatement of scenes.rs
+    cam, _ = osc.camera()
+    primary = RY.camera_rays(cam, n, rng)
+    got, ref, st1 = check_rays(gsc, osc, primary)
+    secondary = RY.secondary_rays(ref, primary, rng)
+    _, ref2, st2 = check_rays(gsc, osc, secondary)
+    tertiary = RY.secondary_rays(ref2, secondary, rng)
+    _, _, st3 = check_rays(gsc, osc, tertiary)
+    assert st1["hits"] > 0.3 * n
+    print(f"scene {number}: {st1} {st2} {st3}")
+
+
+def random_tree(rng, with_media=True):
+    mats = [S.Lambertian((0.5, 0.5, 0.5)), S.Metal((0.8, 0.8, 0.8), 0.3), S.Dielectric(1.5),
+            S.DiffuseLight((4, 4, 4)), S.Lambertian(S.CheckerTexture((0.1, 0.1, 0.1), (0.9, 0.9, 0.9)))]
+
+    def leaf():
+        kind = int(rng.integers(0, 4))
+        m = mats[int(rng.integers(0, len(mats)))]
+        c = tuple(rng.uniform(-20, 20, 3))
+        if kind == 0:
+            return S.Sphere(c, float(rng.uniform(0.3, 4)), m)
+        if kind == 1:
+            return S.MovingSphere((c, tuple(np.array(c) + rng.uniform(-1, 1, 3))), (0, 1), float(rng.uniform(0.3, 2)), m)
+        if kind == 2:
+            plane = [S.XY, S.XZ, S.YZ][int(rng.integers(0, 3))]
+            a0, b0 = rng.uniform(-20, 10, 2)
+            return plane.rectangle(m, (a0, a0 + rng.uniform(1, 15)), (b0, b0 + rng.uniform(1, 15)), float(rng.uniform(-20, 20)))
+        lo = np.array(c)
+        return S.Cube(tuple(lo), tuple(lo + rng.uniform(0.5, 8, 3)), m)
+
+    def node(depth):
+        r = rng.random()
+        if depth >= 3 or r < 0.35:
+            return leaf()
+        if r < 0.55:
+            return S.List([node(depth + 1) for _ in range(int(rng.integers(1, 6)))])
+        if r < 0.7:
+            return S.BvhTree(S.List([leaf() for _ in range(int(rng.integers(1, 40)))]))
+        if r < 0.85:
+            return node(depth + 1).translate(tuple(rng.uniform(-10, 10, 3)))
+        return node(depth + 1).rotate_y(float(rng.uniform(-180, 180)))
+    items = [node(0) for _ in range(int(rng.integers(2, 12)))]
+    if with_media:
+        for _ in range(int(rng.integers(0, 3))):
+            c = np.array(rng.uniform(-10, 10, 3))
+            choice = rng.random()
+            if choice < 0.34:
+                b = S.Sphere(tuple(c), float(rng.uniform(2, 8)), mats[2])
+            elif choice < 0.67:
+                b = S.Cube(tuple(c), tuple(c + rng.uniform(2, 8, 3)), mats[0]).rotate_y(float(rng.uniform(-90, 90))).translate(tuple(rng.uniform(-5, 5, 3)))
+            else:
+                b = S.MovingSphere((tuple(c), tuple(c + 1.0)), (0, 1), 3.0, mats[0])
+            med = S.ConstantMedium(b, float(rng.uniform(0.01, 0.5)), (0.5, 0.5, 0.5))
+            items.append(med if rng.random() < 0.7 else med.rotate_y(float(rng.uniform(-45, 45))).translate(tuple(rng.uniform(-3, 3, 3))))
+    return S.List(items)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fixed_rays_random_scene_trees(ctx, seed):
+    """Arbitrary trees of the reference's API: nested List / BvhTree / translate / rotate_y chains,
+    instanced media, dielectric under wrappers — everything the description can express."""
+    rng = np.random.default_rng(1000 + seed)
+    desc = S.Scene(random_tree(rng)).to_desc()
+    gsc, osc = both(ctx, desc, bvh_seed=seed)
+    n = 30000
+    o = rng.uniform(-40, 40, (n, 3))
+    target = rng.uniform(-15, 15, (n, 3))
+    rays = O.make_rays(o, target - o, time=rng.random(n), xi=rng.random(n) * 0.999 + 0.0005)
+    rays["t_min"] = np.where(rng.random(n) < 0.2, -np.inf, 0.001)  # also the (-inf, x) ranges media use
+    got, ref, st = check_rays(gsc, osc, rays)
+    sec = RY.secondary_rays(ref, rays, rng)
+    if sec.shape[0]:
+        check_rays(gsc, osc, sec)
+    assert st["hits"] > 0.2 * n
+
+
+def test_ten_million_rays_final_scene(ctx, earth_rgba):
+    """BASELINE.json's size: 10^7 rays on the final scene, resident on the device. Checked through
+    size-independent properties plus a 10^5 subsample against the oracle."""
+    import torch
+    n = 10_000_000
+    rng = np.random.default_rng(0xF17ED + 9)
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(9))
+    osc = O.OracleScene.builtin(9, earth=earth_rgba)
+    cam, _ = osc.camera()
+    half = n // 2
+    primary = RY.camera_rays(cam, half, rng)
+    d_rays = torch.from_numpy(primary.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(half * 88, dtype=torch.uint8, device="cuda")
+    gsc.trace_device(d_rays, d_hits, half)
+    h1 = d_hits.cpu().numpy().view(abi.HIT_DTYPE)
+    secondary = RY.secondary_rays(h1, primary, rng)
+    m = secondary.shape[0]
+    assert m > 0.9 * half  # the fog sphere encloses the scene: nearly every ray hits something
+    d_rays2 = torch.from_numpy(secondary.view(np.uint8).reshape(-1)).cuda()
+    d_hits2 = torch.empty(m * 88, dtype=torch.uint8, device="cuda")
+    gsc.trace_device(d_rays2, d_hits2, m)
+    h2 = d_hits2.cpu().numpy().view(abi.HIT_DTYPE)
+    for rays, hits in ((primary, h1), (secondary, h2)):
+        hit = hits["prim_id"] >= 0
+        # p = o + t d for everything except instanced geometry (whose p is Q14-displaced)
+        p = rays["origin"] + hits["t"][:, None] * rays["direction"]
+        plain = hit & (hits["prim_id"] < 2411)  # ids >= 2411: the 1000 instanced spheres
+        assert np.allclose(p[plain], hits["p"][plain], rtol=1e-9, atol=1e-6)
+        assert (hits["t"][hit] >= 0.001).all() and np.isfinite(hits["t"][hit]).all()
+        # ground-box rectangles (ids < 2400): the hit point lies on the plane the id names
+        assert ((hits["prim_id"] >= -1) & (hits["prim_id"] < 3411)).all()
+        # idempotence: nothing is closer than the reported hit
+        sub = rng.choice(np.nonzero(hit)[0], 200000, replace=False)
+        again = rays[sub].copy()
+        again["t_max"] = hits["t"][sub] * (1 - 1e-9)
+        again["xi"] = 1e-300  # an (essentially) infinite free flight: media never scatter
+        solid = hits["material"][sub] >= 0
+        res = gsc.trace(again[solid])
+        assert (res["prim_id"] == abi.RTX_MISS).mean() > 0.9999
+    sub = rng.choice(m, 100000, replace=False)
+    ref, fragile = osc.trace(secondary[sub])
+    RY.compare_hits(h2[sub], ref, fragile)
+
+
+# ---------------------------------------------------------------------------
+# renders
+# ---------------------------------------------------------------------------
+def psnr(a_u8, b_u8):
+    mse = np.mean((a_u8[..., :3].astype(np.float64) - b_u8[..., :3].astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10.0 * math.log10(255.0 ** 2 / mse)
+
+
+def gpu_sum(gsc, w, h, spp, seed=1, max_depth=50, chunk=None):
+    acc = gsc.new_accum(w, h)
+    chunk = chunk or spp
+    for b in range(0, spp, chunk):
+        gsc.render_into(acc, b, min(chunk, spp - b), seed=seed, max_depth=max_depth)
+    return acc
+
+
+def test_furnace_and_tonemap(ctx):
+    albedo, bg = (0.5, 0.25, 0.75), (0.8, 0.6, 0.4)
+    cam = S.CameraDescriptor(lookfrom=(0, 0, -4), lookat=(0, 0, 0), vertical_fov=60.0)
+    desc = S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, S.Lambertian(albedo))]), cam, bg).to_desc()
+    gsc, osc = both(ctx, desc)
+    acc = gpu_sum(gsc, 16, 16, 8)
+    img = acc.cpu().numpy()
+    assert np.allclose(img[..., 3], 8.0)
+    assert np.allclose(img[7:9, 7:9, :3] / 8, np.array(albedo) * np.array(bg), rtol=1e-5)
+    assert np.allclose(img[0, 0, :3] / 8, bg, rtol=1e-5)
+    ref, _ = osc.render_sum(16, 16, 8)
+    assert np.allclose(img[..., :3], ref, rtol=1e-4, atol=1e-5)  # same Philox counters on both sides
+    assert np.array_equal(gsc.tonemap(acc), osc.tonemap(ref, 8))
+
+
+@pytest.mark.parametrize("number", [2, 3, 4, 7, 9])
+def test_same_counter_low_depth_render(ctx, number, earth_rgba):
+    """Same (pixel, sample, bounce) Philox counters on both sides: at depth <= 2 the per-pixel sums
+    agree almost everywhere (they differ only where fp32 shading / an f64 rounding flips a branch)."""
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(number))
+    osc = O.OracleScene.builtin(number, earth=earth_rgba)
+    w, h, spp = (64, 36, 4) if number < 6 else (48, 48, 4)
+    for depth in (1, 2):
+        got = gpu_sum(gsc, w, h, spp, seed=3, max_depth=depth).cpu().numpy()[..., :3]
+        ref, _ = osc.render_sum(w, h, spp, seed=3, max_depth=depth)
+        close = np.isclose(got, ref, rtol=2e-3, atol=2e-3).all(axis=2)
+        assert close.mean() > 0.97, (number, depth, close.mean())
+
+
+RENDER_CASES = {  # scene: (width, height, spp)
+    2: (64, 36, 2048), 3: (64, 36, 2048), 4: (64, 36, 2048), 1: (48, 27, 2048),
+    5: (48, 27, 16384), 7: (40, 40, 24576), 8: (32, 32, 24576), 9: (40, 40, 8192),
+}
+
+
+@pytest.mark.parametrize("number", sorted(RENDER_CASES))
+def test_render_parity_psnr(ctx, number, earth_rgba):
+    """BASELINE.json: at equal high spp, PSNR >= 35 dB and mean per-channel error <= 1/255."""
+    w, h, spp = RENDER_CASES[number]
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(number))
+    osc = O.OracleScene.builtin(number, earth=earth_rgba)
+    acc = gpu_sum(gsc, w, h, spp, seed=11, chunk=1024)
+    got = gsc.tonemap(acc)
+    ref_sum, _ = osc.render_sum(w, h, spp, seed=12)  # independent samples: the comparison is statistical
+    ref = osc.tonemap(ref_sum, spp)
+    p = psnr(got, ref)
+    err = np.abs(got[..., :3].astype(np.float64).mean(axis=(0, 1)) - ref[..., :3].astype(np.float64).mean(axis=(0, 1)))
+    print(f"scene {number}: PSNR {p:.2f} dB, mean per-channel error {err} /255")
+    assert p >= 35.0
+    assert (err <= 1.0).all()
+
+
+def test_spp_chunking_and_sharding_invariance(ctx):
+    """Samples are keyed by their global index: 64 spp in one launch == 4 launches of 16 == two
+    'ranks' summed (up to fp32 summation order). Different seeds differ."""
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(7))
+    one = gpu_sum(gsc, 40, 40, 64, seed=5).cpu().numpy()
+    four = gpu_sum(gsc, 40, 40, 64, seed=5, chunk=16).cpu().numpy()
+    assert np.allclose(one, four, rtol=1e-5, atol=1e-5)
+    parts = []
+    for r in range(2):
+        b, c = R.shard_spp(64, r, 2)
+        acc = gsc.new_accum(40, 40)
+        gsc.render_into(acc, b, c, seed=5)
+        parts.append(acc.cpu().numpy())
+    assert np.allclose(parts[0] + parts[1], one, rtol=1e-5, atol=1e-5)
+    other = gpu_sum(gsc, 40, 40, 64, seed=6).cpu().numpy()
+    assert not np.allclose(one[..., :3], other[..., :3])
+
+
+def test_ragged_image_sizes(ctx):
+    """Widths / heights that are not multiples of the 8x4 warp tile."""
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(2))
+    osc = O.OracleScene.builtin(2)
+    for (w, h) in [(1, 1), (7, 3), (9, 5), (33, 17)]:
+        acc = gpu_sum(gsc, w, h, 4, seed=2, max_depth=1).cpu().numpy()
+        ref, _ = osc.render_sum(w, h, 4, seed=2, max_depth=1)
+        assert np.allclose(acc[..., 3], 4.0)
+        assert np.isclose(acc[..., :3], ref, rtol=2e-3, atol=2e-3).mean() > 0.97
+
+
+def test_reduce_tonemap_kernel_single_device(ctx):
+    """The fused sum + tonemap kernel with 'peers' on the same device (the NVLink path is
+    exercised by bench.py --gpus N)."""
+    import ctypes as C
+    import torch
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(7))
+    accs = []
+    for r in range(3):
+        b, c = R.shard_spp(48, r, 3)
+        a = gsc.new_accum(32, 32)
+        gsc.render_into(a, b, c, seed=9)
+        accs.append(a)
+    total = (accs[0] + accs[1] + accs[2])
+    expect = gsc.tonemap(total)
+    out = torch.zeros((32, 32, 4), dtype=torch.uint8, device="cuda")
+    peers = (C.c_void_p * 2)(accs[1].data_ptr(), accs[2].data_ptr())
+    abi.check(ctx.lib.rtx_reduce_tonemap_peers(ctx.h, accs[0].data_ptr(), peers, 2, 32, 32, out.data_ptr()))
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), expect)
+    assert torch.allclose(accs[0], total)

@@ -1,0 +1,202 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+scene flattening + BVH invariants, the builtin scenes agree with the oracle's restatement of
+scenes.rs, PNG I/O, spp sharding (incl. a world_size-2 gloo run). No compute entry point is
+called here (there is no CPU compute path to call)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import rttnw_b200 as R
+from rttnw_b200 import abi
+from rttnw_b200 import scene as S
+from tests import _oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = abi.load()
+    header = open(os.path.join(ROOT, "include", "rttnw_b200.h")).read()
+    declared = set(re.findall(r"\b(rtx_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rtx_status"}
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in abi.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.rtx_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # the sizes written next to the typedefs in include/rttnw_b200.h
+    assert C.sizeof(abi.Node) == 96 and C.sizeof(abi.Material) == 40 and C.sizeof(abi.Texture) == 48
+    assert C.sizeof(abi.Ray) == 80 and C.sizeof(abi.Hit) == 88
+    assert C.sizeof(abi.Perlin) == 256 * 3 * 8 + 3 * 256 * 4
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = abi.load()
+    h = C.c_void_p()
+    assert lib.rtx_ctx_create(0, None, C.byref(h)) == -2  # RTX_ERR_CUDA, not a CPU fallback
+    assert b"cuda" in lib.rtx_last_error().lower()
+    with pytest.raises(abi.RtxError):
+        R.Context(0)
+
+
+def test_scene_table_matches_main_rs():  # src/main.rs:66-183,255
+    expect = {1: (400, 225, 100), 2: (400, 225, 100), 3: (400, 225, 100), 4: (400, 225, 100), 5: (400, 225, 400),
+              6: (600, 600, 200), 7: (600, 600, 200), 8: (600, 600, 200), 9: (800, 800, 10000)}
+    for n, (w, h, s) in expect.items():
+        d = R.scene_defaults(n)
+        assert (d["width"], d["height"], d["samples"], d["max_depth"]) == (w, h, s, 50)
+    assert R.scene_defaults(9)["name"] == "final_scene"
+    with pytest.raises(abi.RtxError, match="There is no scene 10"):
+        R.scene_defaults(10)
+    with pytest.raises(abi.RtxError):
+        R.BuiltinDesc(0)
+
+
+def test_builtin_scenes_flatten_and_match_oracle_inventory(earth_rgba):
+    for n in range(1, 10):
+        desc = R.BuiltinDesc(n)
+        info = R.flatten_check(desc)
+        osc = O.OracleScene.builtin(n, earth=earth_rgba)
+        assert info["prim_ids"] == osc.prim_count, f"scene {n}"
+        cam, bg = osc.camera()
+        assert bytes(cam) == bytes(desc.desc.camera)
+        assert tuple(desc.desc.background) == bg
+    # final scene: 2400 ground rectangles + 1000 instanced spheres + loose primitives
+    info = R.flatten_check(R.BuiltinDesc(9))
+    assert info["records"] >= 3400 and info["bvh_nodes"] < 2 * info["records"]
+
+
+def test_builtin_scene_is_seeded():
+    a, b, c = R.BuiltinDesc(1, seed=5), R.BuiltinDesc(1, seed=5), R.BuiltinDesc(1, seed=6)
+
+    def nodes(d):
+        return bytes((abi.Node * d.desc.n_nodes).from_address(C.addressof(d.desc.nodes.contents)))
+    assert nodes(a) == nodes(b) and nodes(a) != nodes(c)
+
+
+def test_perlin_tables_of_builtin_scene_match_oracle():
+    # scene 3 draws only the Perlin tables: same SplitMix64 stream on both sides
+    desc = R.BuiltinDesc(3, seed=1234)
+    tab = abi.Perlin()
+    O.load().orc_perlin_generate(1234, C.byref(tab))
+    assert bytes(desc.desc.perlins[0]) == bytes(tab)
+
+
+def test_flatten_rejects_malformed_descriptions():
+    mat = S.Lambertian((0.5, 0.5, 0.5))
+    d = S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, mat)])).to_desc()
+    d.desc.nodes[0].material = 7
+    with pytest.raises(abi.RtxError, match="material"):
+        R.flatten_check(d)
+    d = S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, mat)])).to_desc()
+    d.desc.root = 99
+    with pytest.raises(abi.RtxError, match="root"):
+        R.flatten_check(d)
+    inner = S.ConstantMedium(S.Sphere((0, 0, 0), 1.0, mat), 0.1, (1, 1, 1))
+    d = S.Scene(S.List([S.ConstantMedium(inner, 0.1, (1, 1, 1))])).to_desc()
+    with pytest.raises(abi.RtxError, match="ConstantMedium"):
+        R.flatten_check(d)
+
+
+def test_flatten_invariants_on_random_trees():
+    rng = np.random.default_rng(11)
+    mat = S.Lambertian((0.5, 0.5, 0.5))
+    for trial in range(6):
+        items = []
+        for _ in range(int(rng.integers(1, 60))):
+            kind = rng.integers(0, 5)
+            c = tuple(rng.uniform(-50, 50, 3))
+            if kind == 0:
+                items.append(S.Sphere(c, float(rng.uniform(0.1, 5)), mat))
+            elif kind == 1:
+                items.append(S.MovingSphere((c, tuple(np.array(c) + rng.uniform(-2, 2, 3))), (0, 1), 1.0, mat))
+            elif kind == 2:
+                plane = [S.XY, S.XZ, S.YZ][int(rng.integers(0, 3))]
+                a, b = sorted(rng.uniform(-30, 30, 2)), sorted(rng.uniform(-30, 30, 2))
+                items.append(plane.rectangle(mat, a, b, float(rng.uniform(-30, 30))))
+            elif kind == 3:
+                lo = np.array(c)
+                items.append(S.Cube(tuple(lo), tuple(lo + rng.uniform(0.5, 8, 3)), mat)
+                             .rotate_y(float(rng.uniform(-90, 90))).translate(tuple(rng.uniform(-20, 20, 3))))
+            else:
+                group = S.List([S.Sphere(tuple(rng.uniform(-5, 5, 3)), 0.5, mat) for _ in range(int(rng.integers(1, 20)))])
+                items.append(S.BvhTree(group).translate(c))
+        items.append(S.ConstantMedium(S.Cube((0, 0, 0), (3, 3, 3), mat).rotate_y(10.0), 0.2, (1, 1, 1)))
+        info = R.flatten_check(S.Scene(S.List(items)).to_desc())
+        assert info["records"] >= len(items)
+
+
+def test_png_roundtrip_and_decoder_vs_pil(tmp_path, earth_rgba):
+    from PIL import Image
+    mine = R.png_read_rgba8(os.path.join(ROOT, "assets", "earth.png"))
+    assert mine.shape == (600, 1200, 4) and np.array_equal(mine, earth_rgba)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    path = str(tmp_path / "x.png")
+    R.png_write_rgba8(path, img)
+    assert np.array_equal(np.asarray(Image.open(path).convert("RGBA")), img)  # PIL reads what we write
+    assert np.array_equal(R.png_read_rgba8(path), img)
+    # PIL-written files with the other colour types / filters decode identically
+    for mode in ("RGB", "L", "LA", "P"):
+        p2 = str(tmp_path / f"{mode}.png")
+        Image.fromarray(img).convert(mode).save(p2, optimize=True)
+        assert np.array_equal(R.png_read_rgba8(p2), np.asarray(Image.open(p2).convert("RGBA"))), mode
+    with pytest.raises(abi.RtxError):
+        R.png_read_rgba8(str(tmp_path / "missing.png"))
+    # a missing earth.png is the cyan texture, not an error (texture.rs:96-99)
+    d = R.BuiltinDesc(4, earth_png=str(tmp_path / "missing.png"))
+    assert not d.desc.images[0].rgba
+
+
+def test_shard_spp_partitions_exactly():
+    for total in (1, 7, 100, 10000):
+        for ws in (1, 2, 3, 4, 8):
+            parts = [R.shard_spp(total, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == total
+            for (b0, c0), (b1, _) in zip(parts, parts[1:]):
+                assert b0 + c0 == b1
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+import rttnw_b200 as R
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+begin, count = R.shard_spp(101, rank, 2)
+# stand-in accumulators: what each rank would add for its sample range (sum of sample indices, and the count)
+acc = torch.tensor([float(sum(range(begin, begin + count))), float(count)])
+dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+if rank == 0:
+    assert acc.tolist() == [float(sum(range(101))), 101.0], acc
+    print("OK")
+dist.destroy_process_group()
+"""
+
+
+def test_spp_sharding_reduce_world_size_2_gloo(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert b"OK" in outs[0][0]

@@ -271,11 +271,11 @@ def test_white_furnace_convex_lambertian(oracle):
     normal + (point inside the unit ball), which never re-enters a convex body, so every
     sample seeing the sphere returns albedo * background exactly (main.rs:26-45, Q2, Q8)."""
     albedo, bg = (0.5, 0.25, 0.75), (0.8, 0.6, 0.4)
-    cam = S.CameraDescriptor(lookfrom=(0, 0, -4), lookat=(0, 0, 0), vertical_fov=20.0)
+    cam = S.CameraDescriptor(lookfrom=(0, 0, -4), lookat=(0, 0, 0), vertical_fov=60.0)
     sc = O.OracleScene.from_desc(S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, S.Lambertian(albedo))]), cam, bg).to_desc())
     img, _ = sc.render_sum(16, 16, 8)
     img /= 8
-    centre = img[6:10, 6:10]
+    centre = img[7:9, 7:9]
     assert np.allclose(centre, np.array(albedo) * np.array(bg), rtol=1e-12)
     assert np.allclose(img[0, 0], bg)
 
