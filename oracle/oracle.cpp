@@ -592,11 +592,21 @@ struct Rect : Hittable {                                                        
     }
     bool hit(const Ray& ray, double tmin, double tmax, HitRecord& rec) const override {
         double t = (k - ray.a.at(k_axis)) / ray.b.at(k_axis);
-        probe_cmp(t, tmin); probe_cmp(t, tmax);
+        if (g_probe.on) {
+            // The decision is (t in range) AND (point in rectangle): it is fragile only if one
+            // factor is marginal while the other holds (or is marginal too) — a plane that ties
+            // in t but is hit far outside its extent (coplanar faces of other boxes) is not.
+            auto nearly = [](double a, double b) { return std::fabs(a - b) <= 1e-9 * std::fmax(1.0, std::fmax(std::fabs(a), std::fabs(b))); };
+            double q0 = ray.a.at(axis0) + t * ray.b.at(axis0), q1 = ray.a.at(axis1) + t * ray.b.at(axis1);
+            bool t_ok = !(t < tmin || t > tmax), t_near = nearly(t, tmin) || nearly(t, tmax);
+            bool p_ok = (a0 <= q0 && q0 < a1) && (b0 <= q1 && q1 < b1);
+            bool p_near = (nearly(q0, a0) || nearly(q0, a1)) && ((b0 <= q1 && q1 < b1) || nearly(q1, b0) || nearly(q1, b1));
+            p_near = p_near || ((nearly(q1, b0) || nearly(q1, b1)) && ((a0 <= q0 && q0 < a1) || nearly(q0, a0) || nearly(q0, a1)));
+            if ((t_near && (p_ok || p_near)) || (p_near && (t_ok || t_near))) g_probe.fragile = true;
+        }
         if (t < tmin || t > tmax) return false;
         double p0 = ray.a.at(axis0) + t * ray.b.at(axis0);
         double p1 = ray.a.at(axis1) + t * ray.b.at(axis1);
-        probe_cmp(p0, a0); probe_cmp(p0, a1); probe_cmp(p1, b0); probe_cmp(p1, b1);
         // Range::contains is half-open: start <= x < end (NaN is never contained)
         if (!(a0 <= p0 && p0 < a1) || !(b0 <= p1 && p1 < b1)) return false;
         rec.u = (p0 - a0) / (a1 - a0);

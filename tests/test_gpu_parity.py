@@ -102,8 +102,13 @@ def test_empty_and_degenerate_inputs(ctx):
     sc, osc = both(ctx, S.Scene(S.List([S.Sphere((0, 0, 0), 1.0, mat), S.XZ.rectangle(mat, (-3, 3), (-3, 3), -1.0)])).to_desc())
     rays = O.make_rays([(0, 0, -5), (0, 0, -5), (0, 5, 0), (0, 0, -5), (1e30, 0, 0)],
                        [(0, 0, 0), (0, 0, 1e-300), (0, -1, 0), (1, 0, 0), (-1, 0, 0)])
-    got, ref = sc.trace(rays), osc.trace(rays)[0]
-    assert np.array_equal(got["prim_id"], ref["prim_id"])  # zero / denormal / axis-aligned directions, far origins
+    got, (ref, fragile) = sc.trace(rays), osc.trace(rays)
+    # zero / denormal / axis-aligned directions, far origins. A zero direction makes every reference
+    # test compare NaNs (Sphere::hit then "hits" at t = NaN) and the 1e30 origin cancels the whole
+    # discriminant: the oracle flags both as grazing ties, where only "no crash, valid id" is required.
+    assert list(fragile) == [True, True, False, False, True]
+    assert np.array_equal(got["prim_id"][~fragile], ref["prim_id"][~fragile])
+    assert ((got["prim_id"] >= -1) & (got["prim_id"] < 2)).all()
 
 
 # ---------------------------------------------------------------------------
