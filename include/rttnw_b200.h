@@ -222,7 +222,9 @@ const char* rtx_last_error(void);
 int rtx_device_count(int* count);
 
 /* ---- context: one per GPU. `stream` is a cudaStream_t to launch on (e.g. the
- * caller's torch stream) or NULL to let the context create its own. ---- */
+ * caller's torch stream) or NULL to let the context create its own non-blocking
+ * stream. To launch on the default stream pass the explicit handles
+ * cudaStreamLegacy ((void*)0x1) or cudaStreamPerThread ((void*)0x2). ---- */
 int rtx_ctx_create(int device, void* stream, rtx_ctx** out);
 int rtx_ctx_destroy(rtx_ctx* ctx);
 int rtx_ctx_sync(rtx_ctx* ctx);

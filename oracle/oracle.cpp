@@ -77,17 +77,31 @@ struct Sampler {
 };
 static thread_local Sampler g_sampler;
 
-// Fragility probe: records whether any comparison the reference makes while
-// answering a fixed ray was within 1e-9 relative of flipping.
+// Fragility probe: records whether any comparison the reference makes while answering a fixed
+// ray was within 1e-9 relative of flipping, and the distance `t` of the candidate hit the
+// comparison was about. The closest hit is the minimum over accepted candidates, so a marginal
+// decision about a candidate FARTHER than the final hit cannot change the answer (e.g. a box face
+// coplanar with the floor behind the face that is actually hit); orc_trace_rays reports a ray as
+// fragile only if a marginal candidate lies at or before the final t (or nothing was hit).
+// Comparisons made inside a ConstantMedium's boundary queries decide the medium's own segment,
+// not a candidate at their t, so they always count (nested > 0).
 struct Probe {
     bool on = false;
     bool fragile = false;
+    int nested = 0;
+    double min_t = INFINITY;
 };
 static thread_local Probe g_probe;
-static inline void probe_cmp(double a, double b) {
+static inline void probe_mark(double t) {
+    g_probe.fragile = true;
+    if (g_probe.nested > 0 || !(t == t)) t = -INFINITY;
+    g_probe.min_t = std::fmin(g_probe.min_t, t);
+}
+static inline void probe_cmp(double a, double b, double t) {
     if (!g_probe.on) return;
+    if (std::isinf(a) || std::isinf(b)) return;  // a bound of +-inf (ConstantMedium's queries, t_max) is never marginal
     double m = std::fmax(1.0, std::fmax(std::fabs(a), std::fabs(b)));
-    if (std::fabs(a - b) <= 1e-9 * m) g_probe.fragile = true;
+    if (std::fabs(a - b) <= 1e-9 * m) probe_mark(t);
 }
 
 // ---------------------------------------------------------------------------
@@ -172,7 +186,8 @@ struct Bound {
             if (inv < 0.0) std::swap(t0, t1);
             tmin = std::fmax(t0, tmin);  // f64::max ignores NaN, like fmax
             tmax = std::fmin(t1, tmax);
-            probe_cmp(tmax, tmin);
+            // no fragility probe here: a marginal box cull only matters if something inside is hit at that
+            // same marginal t, and every primitive test below probes its own t / range comparisons
             if (tmax < tmin) return false;
         }
         return true;
@@ -414,15 +429,15 @@ struct Sphere : Hittable {                                                      
         double a = ray.b.dot(ray.b);
         double half_b = oc.dot(ray.b);
         double c = oc.dot(oc) - radius * radius;
-        probe_cmp(half_b * half_b, a * c);
+        probe_cmp(half_b * half_b, a * c, -half_b / a);
         double disc = half_b * half_b - a * c;
         if (disc < 0.0) return false;
         double sqrtd = std::sqrt(disc);
         double root = (-half_b - sqrtd) / a;
-        probe_cmp(root, tmin); probe_cmp(root, tmax);
+        probe_cmp(root, tmin, root); probe_cmp(root, tmax, root);
         if (root < tmin || tmax < root) {
             root = (-half_b + sqrtd) / a;
-            probe_cmp(root, tmin); probe_cmp(root, tmax);
+            probe_cmp(root, tmin, root); probe_cmp(root, tmax, root);
             if (root < tmin || tmax < root) return false;
         }
         rec.t = root;
@@ -453,15 +468,15 @@ struct MovingSphere : Hittable {                                                
         double a = ray.b.dot(ray.b);
         double half_b = oc.dot(ray.b);
         double c = oc.dot(oc) - radius * radius;
-        probe_cmp(half_b * half_b, a * c);
+        probe_cmp(half_b * half_b, a * c, -half_b / a);
         double disc = half_b * half_b - a * c;
         if (disc < 0.0) return false;
         double sqrtd = std::sqrt(disc);
         double root = (-half_b - sqrtd) / a;
-        probe_cmp(root, tmin); probe_cmp(root, tmax);
+        probe_cmp(root, tmin, root); probe_cmp(root, tmax, root);
         if (root < tmin || tmax < root) {
             root = (-half_b + sqrtd) / a;
-            probe_cmp(root, tmin); probe_cmp(root, tmax);
+            probe_cmp(root, tmin, root); probe_cmp(root, tmax, root);
             if (root < tmin || tmax < root) return false;
         }
         rec.t = root;
@@ -596,13 +611,13 @@ struct Rect : Hittable {                                                        
             // The decision is (t in range) AND (point in rectangle): it is fragile only if one
             // factor is marginal while the other holds (or is marginal too) — a plane that ties
             // in t but is hit far outside its extent (coplanar faces of other boxes) is not.
-            auto nearly = [](double a, double b) { return std::fabs(a - b) <= 1e-9 * std::fmax(1.0, std::fmax(std::fabs(a), std::fabs(b))); };
+            auto nearly = [](double a, double b) { return !std::isinf(a) && !std::isinf(b) && std::fabs(a - b) <= 1e-9 * std::fmax(1.0, std::fmax(std::fabs(a), std::fabs(b))); };
             double q0 = ray.a.at(axis0) + t * ray.b.at(axis0), q1 = ray.a.at(axis1) + t * ray.b.at(axis1);
             bool t_ok = !(t < tmin || t > tmax), t_near = nearly(t, tmin) || nearly(t, tmax);
             bool p_ok = (a0 <= q0 && q0 < a1) && (b0 <= q1 && q1 < b1);
             bool p_near = (nearly(q0, a0) || nearly(q0, a1)) && ((b0 <= q1 && q1 < b1) || nearly(q1, b0) || nearly(q1, b1));
             p_near = p_near || ((nearly(q1, b0) || nearly(q1, b1)) && ((a0 <= q0 && q0 < a1) || nearly(q0, a0) || nearly(q0, a1)));
-            if ((t_near && (p_ok || p_near)) || (p_near && (t_ok || t_near))) g_probe.fragile = true;
+            if ((t_near && (p_ok || p_near)) || (p_near && (t_ok || t_near))) probe_mark(t);
         }
         if (t < tmin || t > tmax) return false;
         double p0 = ray.a.at(axis0) + t * ray.b.at(axis0);
@@ -732,17 +747,25 @@ struct ConstantMedium : Hittable {                                              
     }
     bool hit(const Ray& ray, double tmin, double tmax, HitRecord& rec) const override {
         HitRecord r1, r2;
-        if (!boundary->hit(ray, -INFINITY, INFINITY, r1)) return false;
-        if (!boundary->hit(ray, r1.t + 0.0001, INFINITY, r2)) return false;
+        g_probe.nested++;
+        bool in = boundary->hit(ray, -INFINITY, INFINITY, r1) && boundary->hit(ray, r1.t + 0.0001, INFINITY, r2);
+        g_probe.nested--;
+        if (!in) return false;
         r1.t = std::fmax(r1.t, tmin);
         r2.t = std::fmin(r2.t, tmax);
-        probe_cmp(r1.t, r2.t);
+        if (g_probe.on) {
+            // the candidate this comparison is about is the scatter point, not the entry point: when the far
+            // end was clipped by a surface hit at the entry distance (the glass sphere that is also this
+            // medium's boundary, scenes.rs:282-292), the surface wins whichever is tested first
+            double entry = std::fmax(r1.t, 0.);
+            probe_cmp(r1.t, r2.t, entry + neg_inv_density * std::log(g_sampler.medium_u(medium_key)) / ray.b.magnitude());
+        }
         if (r1.t >= r2.t) return false;
         r1.t = std::fmax(r1.t, 0.);
         double ray_length = ray.b.magnitude();
         double distance_inside = (r2.t - r1.t) * ray_length;
         double hit_distance = neg_inv_density * std::log(g_sampler.medium_u(medium_key));
-        probe_cmp(hit_distance, distance_inside);
+        probe_cmp(hit_distance, distance_inside, r1.t);
         if (hit_distance > distance_inside) return false;
         rec.t = r1.t + hit_distance / ray_length;
         rec.p = ray.at(rec.t);
@@ -1172,10 +1195,15 @@ void orc_trace_rays(const orc_scene* s, int64_t n, const rtx_ray* rays, rtx_hit*
             Ray ray{Vec3(r.origin[0], r.origin[1], r.origin[2]), Vec3(r.direction[0], r.direction[1], r.direction[2]), r.time};
             g_sampler.xi = r.xi;
             g_probe.fragile = false;
+            g_probe.nested = 0;
+            g_probe.min_t = INFINITY;
             HitRecord rec;
             rtx_hit& h = hits[i];
             std::memset(&h, 0, sizeof(h));
-            if (s->world->hit(ray, r.t_min, r.t_max, rec)) {
+            bool got = s->world->hit(ray, r.t_min, r.t_max, rec);
+            bool relevant = g_probe.fragile;  // a miss: every marginal decision counts
+            if (got) {
+                relevant = g_probe.fragile && !(g_probe.min_t > rec.t + 1e-9 * std::fmax(1.0, std::fabs(rec.t)));
                 h.prim_id = rec.prim_id;
                 h.material = rec.material ? rec.material->index : -1;
                 h.front_face = rec.front_face ? 1 : 0;
@@ -1187,7 +1215,7 @@ void orc_trace_rays(const orc_scene* s, int64_t n, const rtx_ray* rays, rtx_hit*
                 h.prim_id = RTX_MISS;
                 h.material = -1;
             }
-            if (fragile) fragile[i] = g_probe.fragile ? 1 : 0;
+            if (fragile) fragile[i] = relevant ? 1 : 0;
         }
         g_probe.on = false;
     });

@@ -88,7 +88,10 @@ class Context:
         torch.cuda.set_device(device)
         self.stream = torch.cuda.current_stream(device)
         self.h = C.c_void_p()
-        abi.check(self.lib.rtx_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self.h)))
+        # torch's default stream has handle 0, which the ABI reads as "create your own": name it explicitly
+        # (cudaStreamLegacy == 0x1) so that kernels, torch tensors and torch events share one stream order
+        handle = self.stream.cuda_stream or 0x1
+        abi.check(self.lib.rtx_ctx_create(device, C.c_void_p(handle), C.byref(self.h)))
 
     def sync(self) -> None:
         abi.check(self.lib.rtx_ctx_sync(self.h))
