@@ -569,7 +569,21 @@ struct BvhTree : Hittable {                                                     
         return build(objects, 0, objects.size(), 0., 1., rng);
     }
     bool hit(const Ray& ray, double tmin, double tmax, HitRecord& rec) const override { // hittable.rs:355-368
-        if (!bound.hit(ray, tmin, tmax)) return false;
+        if (!bound.hit(ray, tmin, tmax)) {
+            // Fragility probe only: a box culled by a whisker (its entry distance within a few 1e-9 of
+            // t_max — 1/d rounding decides) may hide a primitive that ties with the closest hit so far,
+            // e.g. the coplanar side faces adjacent ground boxes share. Look inside with the interval
+            // widened; whatever would have been accepted there is a marginal candidate at its own t.
+            if (g_probe.on && std::isfinite(tmax)) {
+                double wide = tmax + 4e-9 * std::fmax(1.0, std::fabs(tmax));
+                if (bound.hit(ray, tmin, wide)) {
+                    HitRecord shadow;
+                    if (left->hit(ray, tmin, wide, shadow)) probe_mark(shadow.t);
+                    if (left.get() != right.get() && right->hit(ray, tmin, wide, shadow)) probe_mark(shadow.t);
+                }
+            }
+            return false;
+        }
         HitRecord lrec, rrec;
         bool hl = left->hit(ray, tmin, tmax, lrec);
         // span-1 nodes have left == right (hittable.rs:282-285): the reference tests the same

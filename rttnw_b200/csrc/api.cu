@@ -41,10 +41,11 @@ struct rtx_ctx {
     int sm_count = 0;
     unsigned int* d_work_counter = nullptr;  // render_kernel's tile dispenser
     rtx::Counters* d_counters = nullptr;
+    int w_node = 1, w_leaf = 1, w_shade = 1;  // render_kernel phase weights (RTX_W_NODE / RTX_W_LEAF / RTX_W_SHADE override)
 };
 
 struct rtx_scene {
-    rtx_ctx* ctx = nullptr;
+    int device = 0;  // not the ctx: a scene may outlive the context that created it
     rtx::SceneView view{};
     rtx::CameraView camera{};
     void* d_arena = nullptr;
@@ -90,6 +91,14 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     e = cudaMalloc(&c->d_work_counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(rtx::Counters));
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc"); }
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = std::getenv(name);
+        int x = v ? std::atoi(v) : dflt;
+        return x > 0 ? x : dflt;
+    };
+    c->w_node = env_int("RTX_W_NODE", c->w_node);
+    c->w_leaf = env_int("RTX_W_LEAF", c->w_leaf);
+    c->w_shade = env_int("RTX_W_SHADE", c->w_shade);
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -126,7 +135,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     if (!rtx::flatten_scene(*desc, fs, err)) return fail(RTX_ERR_INVALID, "scene description: " + err);
     rtx_scene* s = new (std::nothrow) rtx_scene();
     if (!s) return fail(RTX_ERR_NOMEM, "out of host memory");
-    s->ctx = c;
+    s->device = c->device;
     auto bail = [&](int code) { rtx_scene_destroy(s); return code; };
 
     // images -> point-sampled texture objects (ImageTexture, texture.rs:61-107)
@@ -170,7 +179,8 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     size_t off_texs = align(off_mats + fs.materials.size() * sizeof(rtx::DMaterial));
     size_t off_perlins = align(off_texs + fs.textures.size() * sizeof(rtx::DTexture));
     size_t off_images = align(off_perlins + fs.perlins.size() * sizeof(rtx::DPerlin));
-    size_t total = align(off_images + dimages.size() * sizeof(rtx::DImage)) + 256;
+    size_t off_media = align(off_images + dimages.size() * sizeof(rtx::DImage));
+    size_t total = align(off_media + fs.media.size() * sizeof(rtx::DMedium)) + 256;
     std::vector<uint8_t> host(total, 0);
     auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(host.data() + off, src, bytes); };
     put(off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(rtx::BvhNode));
@@ -180,6 +190,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     put(off_texs, fs.textures.data(), fs.textures.size() * sizeof(rtx::DTexture));
     put(off_perlins, fs.perlins.data(), fs.perlins.size() * sizeof(rtx::DPerlin));
     put(off_images, dimages.data(), dimages.size() * sizeof(rtx::DImage));
+    put(off_media, fs.media.data(), fs.media.size() * sizeof(rtx::DMedium));
     cudaError_t e = cudaMalloc(&s->d_arena, total);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scene)"));
     s->arena_bytes = total;
@@ -194,6 +205,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->view.textures = (const rtx::DTexture*)(base + off_texs);
     s->view.perlins = (const rtx::DPerlin*)(base + off_perlins);
     s->view.images = (const rtx::DImage*)(base + off_images);
+    s->view.media = (const rtx::DMedium*)(base + off_media);
     s->view.world_root = fs.world_root;
     s->view.n_media = fs.n_media;
     s->camera = fs.camera;
@@ -206,10 +218,8 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
 
 int rtx_scene_destroy(rtx_scene* s) {
     if (!s) return RTX_OK;
-    if (s->ctx) {
-        cudaSetDevice(s->ctx->device);
-        cudaStreamSynchronize(s->ctx->stream);
-    }
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();  // kernels still reading the arena (any stream)
     for (auto t : s->textures) cudaDestroyTextureObject(t);
     for (auto a : s->arrays) cudaFreeArray(a);
     if (s->d_arena) cudaFree(s->d_arena);
@@ -294,6 +304,7 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     if (p->width <= 0 || p->height <= 0 || p->spp_count < 0 || p->spp_begin < 0 || p->max_depth < 0)
         return fail(RTX_ERR_INVALID, "bad render parameters");
     if ((int64_t)p->width * p->height > 0x7fffffff) return fail(RTX_ERR_INVALID, "image too large");
+    if (p->spp_count > (1 << 26)) return fail(RTX_ERR_INVALID, "more than 2^26 samples per pixel in one call");
     if (p->spp_count == 0) return RTX_OK;
     CU(cudaSetDevice(c->device));
     rtx::RenderArgs a;
@@ -304,22 +315,24 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     a.k0 = (uint32_t)p->seed; a.k1 = (uint32_t)(p->seed >> 32);
     a.tiles_x = (p->width + rtx::kTileW - 1) / rtx::kTileW;
     a.tiles_y = (p->height + rtx::kTileH - 1) / rtx::kTileH;
+    a.w_node = c->w_node; a.w_leaf = c->w_leaf; a.w_shade = c->w_shade;
     CU(cudaMemsetAsync(c->d_work_counter, 0, sizeof(unsigned int), c->stream));
     // persistent grid: as many CTAs as fit, a whole number per SM
     int per_sm = 0;
-    if (counted) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::render_kernel<true>, 128, 0));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::render_kernel<false>, 128, 0));
+    if (counted) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::render_kernel<true>, rtx::kRenderBlock, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::render_kernel<false>, rtx::kRenderBlock, 0));
     if (per_sm < 1) per_sm = 1;
     int64_t n_tiles = (int64_t)a.tiles_x * a.tiles_y;
     int64_t grid = (int64_t)c->sm_count * per_sm;
-    int64_t needed = (n_tiles + 3) / 4;
+    const int warps = rtx::kRenderBlock / 32;
+    int64_t needed = (n_tiles + warps - 1) / warps;
     if (grid > needed) grid = needed;
     if (grid < 1) grid = 1;
     float4* acc = reinterpret_cast<float4*>(d_accum);
     if (counted)
-        rtx::render_kernel<true><<<(unsigned)grid, 128, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, c->d_counters);
+        rtx::render_kernel<true><<<(unsigned)grid, rtx::kRenderBlock, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, c->d_counters);
     else
-        rtx::render_kernel<false><<<(unsigned)grid, 128, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, nullptr);
+        rtx::render_kernel<false><<<(unsigned)grid, rtx::kRenderBlock, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, nullptr);
     CU(cudaGetLastError());
     return RTX_OK;
 }

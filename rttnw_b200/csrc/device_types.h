@@ -17,6 +17,7 @@ struct alignas(16) BvhNode {
     int32_t _pad[2];
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+constexpr int kTraversalStack = 64;   // per-thread traversal stack entries; the flattener refuses deeper scenes
 constexpr int32_t kEmptyChild = ~0;  // leaf with count 0 (its box is inverted, never hit)
 
 enum RecType : int32_t {
@@ -28,7 +29,8 @@ enum RecType : int32_t {
     REC_INSTANCE = 5,  // a = BVH root of the instanced group, b = chain length, c = chain begin
     REC_MEDIUM = 6     // a = phase texture, b = prim id, c = boundary BVH root (or -1: the boundary is
                        // the untransformed sphere d[4..7] = {cx, cy, cz, r});
-                       // d = {neg_inv_density, medium ordinal, outer chain begin, outer chain len}
+                       // d = {neg_inv_density, medium ordinal, outer chain begin, outer chain len}.
+                       // Medium records are not BVH leaves: they are listed in SceneView::media.
 };
 
 // One 96-byte record per leaf primitive / instance / medium. Geometry is f64: the reference
@@ -75,6 +77,18 @@ struct alignas(16) DPerlin {
     uint8_t perm[3][256];
 };
 
+// ConstantMedium (hittable.rs:724-801) entries. Every ray evaluates every medium whose (fp32,
+// outward-rounded) world bounds it crosses BEFORE the surface traversal: the medium's scatter
+// distance is a candidate like any other hit and the closest candidate wins, which is what the
+// reference's `closest`-clipped test computes whatever the list order (SURVEY.md hard parts).
+struct alignas(16) DMedium {
+    float lo[3];
+    int32_t record;  // index of the REC_MEDIUM record
+    float hi[3];
+    int32_t _pad;
+};
+static_assert(sizeof(DMedium) == 32, "DMedium must be 32 bytes");
+
 struct DImage {
     unsigned long long tex;  // cudaTextureObject_t (0: failed load -> cyan)
     int32_t width, height;
@@ -89,6 +103,7 @@ struct SceneView {
     const DTexture* textures;
     const DPerlin* perlins;
     const DImage* images;
+    const DMedium* media;
     int32_t world_root;
     int32_t n_media;  // > 0: rays draw one Philox MEDIUM block per 4 media
 };

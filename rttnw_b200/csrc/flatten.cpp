@@ -7,8 +7,9 @@
 //   * leaf records (sphere / moving sphere / rectangle; a Cube becomes its six rectangles
 //     in the order of Cube::new, :560-569),
 //   * one transform chain per distinct wrapper path (outermost op first),
-//   * a BVH per instanced group, one over the world (identity-chain primitives, instance
-//     records, medium records) and one per ConstantMedium boundary.
+//   * a BVH per instanced group, one over the world (identity-chain primitives and instance
+//     records) and one per ConstantMedium boundary; the media themselves are a short list
+//     with world bounds that every ray checks before it traverses (device_types.h, DMedium).
 // Bounds are geometrically correct rotated bounds — NOT YRotate::new's (:654-672),
 // which the reference never uses for culling either.
 #include "flatten.hpp"
@@ -41,7 +42,7 @@ namespace {
 struct Item {
     Record rec;
     Aabb box;
-    bool solo() const { return rec.type == REC_INSTANCE || rec.type == REC_MEDIUM; }  // must sit alone in its leaf
+    bool solo() const { return rec.type == REC_INSTANCE; }  // must sit alone in its leaf
 };
 
 float round_down(double v) {
@@ -188,13 +189,15 @@ struct BvhBuilder {
         for (int i = 0; i < t.count; ++i) records.push_back(items[(size_t)order[(size_t)(t.first + i)]].rec);
         return ~((first << 4) | t.count);
     }
-    int32_t emit(int ti) {  // ti is an inner tmp node
+    int depth = 0;  // inner nodes on the longest root-to-leaf path (set by build)
+    int32_t emit(int ti, int level = 1) {  // ti is an inner tmp node
+        depth = std::max(depth, level);
         int32_t idx = (int32_t)nodes.size();
         nodes.push_back(BvhNode{});
         int kids[2] = {tmp[(size_t)ti].left, tmp[(size_t)ti].right};
         for (int k = 0; k < 2; ++k) {
             const Tmp ct = tmp[(size_t)kids[k]];
-            int32_t ref = ct.left < 0 ? emit_leaf(ct) : emit(kids[k]);
+            int32_t ref = ct.left < 0 ? emit_leaf(ct) : emit(kids[k], level + 1);
             BvhNode& n = nodes[(size_t)idx];
             set_child_box(n, k, ct.box);
             (k == 0 ? n.child0 : n.child1) = ref;
@@ -204,6 +207,7 @@ struct BvhBuilder {
     // Returns the root node index; `bounds` gets the f64 bounds of everything.
     int32_t build(Aabb& bounds) {
         bounds.reset();
+        depth = 1;
         for (const auto& it : items) bounds.grow(it.box);
         order.resize(items.size());
         for (size_t i = 0; i < items.size(); ++i) order[i] = (int)i;
@@ -434,8 +438,11 @@ struct Flattener {
         }
     }
 
+    // Stack entries a traversal of this world can need: the sentinel, one deferred sibling per level of
+    // the top BVH, the two entries an instance pushes, one per level of the deepest instanced BVH.
     int32_t build_world(World& w, Aabb& bounds) {
         std::vector<Item> top;
+        int inst_depth = 0;
         for (const auto& path : w.paths) {
             Group& g = w.groups[path];
             if (path.empty()) {
@@ -445,6 +452,7 @@ struct Flattener {
             Aabb ob;
             BvhBuilder b(out.nodes, out.records, g.items);
             int32_t root = b.build(ob);
+            inst_depth = std::max(inst_depth, b.depth);
             Item inst;
             std::memset(&inst.rec, 0, sizeof(inst.rec));
             inst.rec.type = REC_INSTANCE;
@@ -468,9 +476,20 @@ struct Flattener {
             }
             top.push_back(inst);
         }
-        for (auto& m : w.media) top.push_back(m);
         BvhBuilder b(out.nodes, out.records, top);
-        return b.build(bounds);
+        int32_t root = b.build(bounds);
+        out.max_stack = std::max(out.max_stack, 1 + b.depth + 2 + inst_depth + 1);
+        // media: records outside every BVH + a bounds list (only the main world has any)
+        for (auto& m : w.media) {
+            DMedium dm;
+            std::memset(&dm, 0, sizeof(dm));
+            for (int i = 0; i < 3; ++i) { dm.lo[i] = round_down(m.box.lo[i]); dm.hi[i] = round_up(m.box.hi[i]); }
+            dm.record = (int32_t)out.records.size();
+            out.records.push_back(m.rec);
+            out.media.push_back(dm);
+            bounds.grow(m.box);
+        }
+        return root;
     }
 
     bool run() {
@@ -538,7 +557,8 @@ struct Flattener {
         std::vector<XformOp> chain;
         if (!collect(d.root, path, chain, w, 0)) return false;
         out.world_root = build_world(w, out.world_bounds);
-        out.n_media = next_medium;
+        if (out.max_stack > kTraversalStack) return fail("BVH deeper than the device traversal stack");
+        out.n_media = (int32_t)out.media.size();
         out.n_prims = next_prim;
         camera_view(d.camera, d.background, out.camera);
         return true;
@@ -664,10 +684,6 @@ struct Checker {
                         if (r.c < 0 || r.c + r.b > (int)fs.xforms.size()) return fail("instance chain out of range");
                         int sub = 0;
                         if (!walk(r.a, depth + 1, sub)) return false;
-                    } else if (r.type == REC_MEDIUM) {
-                        if (r.a < 0 || r.a >= (int)fs.textures.size()) return fail("medium texture out of range");
-                        int sub = 0;
-                        if (r.c >= 0 && !walk(r.c, depth + 1, sub)) return false;  // -1: analytic sphere boundary
                     } else {
                         return fail("unknown record type");
                     }
@@ -683,6 +699,16 @@ bool check_flat_scene(const FlatScene& fs, std::string& err) {
     Checker c{fs, err, std::vector<int>(fs.nodes.size(), 0), std::vector<int>(fs.records.size(), 0)};
     int n = 0;
     if (!c.walk(fs.world_root, 0, n)) return false;
+    for (const DMedium& m : fs.media) {  // media: listed, not in a BVH; their boundary BVHs are walked here
+        if (m.record < 0 || m.record >= (int32_t)fs.records.size()) { err = "medium record out of range"; return false; }
+        const Record& r = fs.records[(size_t)m.record];
+        if (r.type != REC_MEDIUM) { err = "media list entry is not a medium record"; return false; }
+        if (c.rec_seen[(size_t)m.record]++) { err = "medium record listed twice"; return false; }
+        if (r.a < 0 || r.a >= (int)fs.textures.size()) { err = "medium texture out of range"; return false; }
+        int sub = 0;
+        if (r.c >= 0 && !c.walk(r.c, 0, sub)) return false;  // -1: analytic sphere boundary
+    }
+    if (fs.max_stack > kTraversalStack) { err = "BVH too deep for the traversal stack"; return false; }
     for (size_t i = 0; i < fs.records.size(); ++i)
         if (c.rec_seen[i] != 1) { err = "record not reachable from the world root"; return false; }
     for (size_t i = 0; i < fs.nodes.size(); ++i)

@@ -27,6 +27,8 @@ struct FlatScene {
     std::vector<DMaterial> materials;
     std::vector<DTexture> textures;
     std::vector<DPerlin> perlins;
+    std::vector<DMedium> media;  // in medium-ordinal order
+    int32_t max_stack = 0;       // traversal stack entries the deepest root-to-leaf path can need
     int32_t world_root = 0;
     int32_t n_media = 0;
     int32_t n_prims = 0;  // number of primitive ids handed out

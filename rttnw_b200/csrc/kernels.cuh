@@ -95,17 +95,14 @@ struct Tally<true> {
 };
 
 // ---------------------------------------------------------------------------
-// The ray expressed in the space currently being traversed: f64 for the primitive
-// tests, fp32 directed-rounding slab parameters for the BVH boxes.
+// The fp32 half of a ray in the space currently being traversed: directed-rounding slab
+// parameters for the BVH boxes. The f64 half (origin, direction) is the ray itself, or the ray
+// pushed through the instance's transform chain when a leaf inside an instance is tested.
 // ---------------------------------------------------------------------------
-struct Space {
-    d3 o, d;        // f64 origin / direction in this space
-    d3 inv_d;       // 1 / d (f64), for the rectangle plane distance
-    double inv_a;   // 1 / dot(d, d), for the sphere roots
+struct SlabRay {
     float idx, idy, idz;     // fp32 1/d, magnitude clamped to 2^100
     float anx, any, anz;     // near offsets: round-down of -o * idx
     float afx, afy, afz;     // far offsets:  round-up   of -o * idx
-    bool sx, sy, sz;         // direction component negative: near plane is the box's hi
 };
 
 __device__ __forceinline__ float clamp_inv(float d) {
@@ -113,11 +110,7 @@ __device__ __forceinline__ float clamp_inv(float d) {
     if (!(fabsf(inv) <= 0x1p100f)) inv = copysignf(0x1p100f, d);
     return inv;
 }
-__device__ __forceinline__ void make_space(d3 o, d3 d, Space& s) {
-    s.o = o;
-    s.d = d;
-    s.inv_d = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
-    s.inv_a = 1.0 / dot(d, d);
+__device__ __forceinline__ void make_slab(d3 o, d3 d, SlabRay& s) {
     s.idx = clamp_inv((float)d.x);
     s.idy = clamp_inv((float)d.y);
     s.idz = clamp_inv((float)d.z);
@@ -125,20 +118,18 @@ __device__ __forceinline__ void make_space(d3 o, d3 d, Space& s) {
     s.anx = __double2float_rd(ax); s.afx = __double2float_ru(ax);
     s.any = __double2float_rd(ay); s.afy = __double2float_ru(ay);
     s.anz = __double2float_rd(az); s.afz = __double2float_ru(az);
-    s.sx = s.idx < 0.0f;
-    s.sy = s.idy < 0.0f;
-    s.sz = s.idz < 0.0f;
 }
 
 // Conservative fp32 version of Bound::hit (bound.rs:13-32): never rejects a box the f64
 // test would accept. lo/hi are rounded outward at build time, the offsets are rounded
 // outward per ray, and the interval is widened by 2^-21 relative for the fma / reciprocal
 // roundings. Returns the (widened) entry distance through `tnear`.
-__device__ __forceinline__ bool slab(const Space& s, float lox, float hix, float loy, float hiy, float loz, float hiz,
+__device__ __forceinline__ bool slab(const SlabRay& s, float lox, float hix, float loy, float hiy, float loz, float hiz,
                                      float tmin, float tmax, float& tnear) {
-    float nx = fmaf(s.sx ? hix : lox, s.idx, s.anx), fx = fmaf(s.sx ? lox : hix, s.idx, s.afx);
-    float ny = fmaf(s.sy ? hiy : loy, s.idy, s.any), fy = fmaf(s.sy ? loy : hiy, s.idy, s.afy);
-    float nz = fmaf(s.sz ? hiz : loz, s.idz, s.anz), fz = fmaf(s.sz ? loz : hiz, s.idz, s.afz);
+    bool sx = s.idx < 0.0f, sy = s.idy < 0.0f, sz = s.idz < 0.0f;  // negative direction: the near plane is the box's hi
+    float nx = fmaf(sx ? hix : lox, s.idx, s.anx), fx = fmaf(sx ? lox : hix, s.idx, s.afx);
+    float ny = fmaf(sy ? hiy : loy, s.idy, s.any), fy = fmaf(sy ? loy : hiy, s.idy, s.afy);
+    float nz = fmaf(sz ? hiz : loz, s.idz, s.anz), fz = fmaf(sz ? loz : hiz, s.idz, s.afz);
     float tn = fmaxf(fmaxf(nx, ny), nz);
     float tf = fminf(fminf(fx, fy), fz);
     tn = fmaf(-fabsf(tn), 0x1p-21f, tn);
@@ -156,23 +147,29 @@ __device__ __forceinline__ void apply_op(const XformOp& op, d3& o, d3& d) {
         d = mk(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z);
     }
 }
+// chain = begin | len << 24 (0 = world space)
+__device__ __forceinline__ void to_space(const SceneView& sc, int32_t chain, d3& o, d3& d) {
+    int32_t begin = chain & 0xFFFFFF, len = (uint32_t)chain >> 24;
+    for (int32_t k = 0; k < len; ++k) apply_op(sc.xforms[begin + k], o, d);
+}
 
 // ---------------------------------------------------------------------------
 // Primitive tests: same operations, in the same order, as the reference (f64).
 // They only decide and return t; the hit record is built once, for the winner.
 // ---------------------------------------------------------------------------
 // Sphere::hit / MovingSphere::hit quadratic, hittable.rs:88-108,196-216 (Q9: both ends inclusive)
-__device__ __forceinline__ bool sphere_roots(const Space& s, d3 c, double r, double tmin, double tmax, double& t) {
-    d3 oc = s.o - c;
-    double half_b = dot(oc, s.d);
+__device__ __forceinline__ bool sphere_roots(d3 o, d3 d, d3 c, double r, double tmin, double tmax, double& t) {
+    d3 oc = o - c;
+    double a = dot(d, d);
+    double half_b = dot(oc, d);
     double cc = dot(oc, oc) - r * r;
-    double a = dot(s.d, s.d);
     double disc = half_b * half_b - a * cc;
     if (disc < 0.0) return false;
     double sq = sqrt(disc);
-    double root = (-half_b - sq) * s.inv_a;
+    double inv_a = 1.0 / a;
+    double root = (-half_b - sq) * inv_a;
     if (root < tmin || tmax < root) {
-        root = (-half_b + sq) * s.inv_a;
+        root = (-half_b + sq) * inv_a;
         if (root < tmin || tmax < root) return false;
     }
     t = root;
@@ -183,13 +180,13 @@ __device__ __forceinline__ d3 msphere_center(const double* d, double time) {  //
     return mk(d[0] + f * d[3], d[1] + f * d[4], d[2] + f * d[5]);
 }
 // Rectangle::hit, hittable.rs:503-513 (Q11: t inclusive, ranges half-open, NaN never contained)
-__device__ __forceinline__ bool rect_hit(const Space& s, int plane, const double* d, double tmin, double tmax, double& t) {
+__device__ __forceinline__ bool rect_hit(d3 o, d3 d, int plane, const double* r, double tmin, double tmax, double& t) {
     int a0 = plane == 2 ? 1 : 0, a1 = plane == 0 ? 1 : 2, ak = plane == 0 ? 2 : (plane == 1 ? 1 : 0);
-    double tt = (d[4] - comp(s.o, ak)) * comp(s.inv_d, ak);
+    double tt = (r[4] - comp(o, ak)) / comp(d, ak);
     if (tt < tmin || tt > tmax) return false;
-    double p0 = comp(s.o, a0) + tt * comp(s.d, a0);
-    double p1 = comp(s.o, a1) + tt * comp(s.d, a1);
-    if (!(d[0] <= p0 && p0 < d[1]) || !(d[2] <= p1 && p1 < d[3])) return false;
+    double p0 = comp(o, a0) + tt * comp(d, a0);
+    double p1 = comp(o, a1) + tt * comp(d, a1);
+    if (!(r[0] <= p0 && p0 < r[1]) || !(r[2] <= p1 && p1 < r[3])) return false;
     t = tt;
     return true;
 }
@@ -200,156 +197,191 @@ struct Best {
     int32_t chain;  // transform chain of the instance the record was hit in: begin | len << 24
 };
 
-constexpr int kStackSize = 48;
+constexpr int kStackSize = kTraversalStack;
 constexpr int32_t kSentinel = (int32_t)0x80000000;       // bottom of a query's stack
 constexpr int32_t kLeaveInstance = (int32_t)0x80000001;  // pop: return to the query's own space
 
 __device__ __forceinline__ double ldg_d(const double* p) { return __ldg(p); }
 
-// Closest hit over the BVH rooted at `root` for `ray` in [tmin, best.t].
-// kMedia: ConstantMedium records are evaluated (world query); otherwise they cannot occur
-// (boundary queries). `stack` is a per-thread array, `sp` the first free slot.
-template <bool kMedia, bool kPrecise, bool kCount>
-__device__ __forceinline__ void traverse(const SceneView& sc, int32_t root, const RayD& ray, double tmin, Best& best,
-                                         int32_t* stack, int sp, double medium_xi, const Sampler* smp, Tally<kCount>& tally) {
-    Space s;
-    make_space(ray.o, ray.d, s);
+// One geometric record (sphere / moving sphere / rectangle) against the ray (o, d) of its space.
+template <bool kCount>
+__device__ __forceinline__ bool test_geometry(const Record* rp, int32_t type, d3 o, d3 d, double time, double tmin, double tmax,
+                                              double& t, Tally<kCount>& tally) {
+    const double* q = rp->d;
+    if (type == REC_SPHERE) {
+        tally.sphere();
+        double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
+        return sphere_roots(o, d, mk(a.x, a.y, b.x), b.y, tmin, tmax, t);
+    }
+    if (type == REC_MSPHERE) {
+        tally.sphere();
+        double dd[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dd[k] = ldg_d(q + k);
+        return sphere_roots(o, d, msphere_center(dd, time), dd[6], tmin, tmax, t);
+    }
+    tally.rect();
+    double dd[5];
+    double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
+    dd[0] = a.x; dd[1] = a.y; dd[2] = b.x; dd[3] = b.y; dd[4] = ldg_d(q + 4);
+    return rect_hit(o, d, type - REC_RECT_XY, dd, tmin, tmax, t);
+}
+
+// One inner node: both child boxes against the ray; returns the next node to visit and pushes the
+// farther child when both are hit.
+template <bool kCount>
+__device__ __forceinline__ int32_t node_step(const SceneView& sc, int32_t cur, const SlabRay& s, float tmin_f, float tmax_f,
+                                             int32_t* stack, int& sp, Tally<kCount>& tally) {
+    const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+    int4 meta = __ldg(reinterpret_cast<const int4*>(np + 3));
+    tally.node();
+    float n0, n1;
+    bool h0 = slab(s, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, tmin_f, tmax_f, n0);
+    bool h1 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, n1);
+    if (h0 && h1) {
+        bool swap = n1 < n0;
+        stack[sp++] = swap ? meta.x : meta.y;
+        return swap ? meta.y : meta.x;
+    }
+    if (h0) return meta.x;
+    if (h1) return meta.y;
+    return stack[--sp];
+}
+
+// Closest hit over the BVH rooted at `root` for `ray` in [tmin, best.t]: plain while-while
+// traversal, instances entered by switching the ray's space inside the same loop. Used by the
+// fixed-ray kernel and by ConstantMedium boundary queries (the render kernel runs the batched
+// form of the same steps). `stack` is a per-thread array, `sp` the first free slot.
+template <bool kCount>
+__device__ __forceinline__ void traverse_simple(const SceneView& sc, int32_t root, const RayD& ray, double tmin, Best& best,
+                                                int32_t* stack, int sp, Tally<kCount>& tally) {
+    SlabRay s;
+    make_slab(ray.o, ray.d, s);
+    d3 o = ray.o, d = ray.d;
     float tmin_f = __double2float_rd(tmin);
     float tmax_f = __double2float_ru(best.t);
     int32_t cur_chain = 0;
-    const int sp0 = sp;
     stack[sp++] = kSentinel;
     int32_t cur = root;
     while (true) {
-        // ---- inner nodes ----
-        while (cur >= 0) {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            int4 meta = __ldg(reinterpret_cast<const int4*>(np + 3));
-            tally.node();
-            float n0, n1;
-            bool h0 = slab(s, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, tmin_f, tmax_f, n0);
-            bool h1 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, n1);
-            if (h0 && h1) {
-                bool swap = n1 < n0;
-                stack[sp++] = swap ? meta.x : meta.y;
-                cur = swap ? meta.y : meta.x;
-            } else if (h0) {
-                cur = meta.x;
-            } else if (h1) {
-                cur = meta.y;
-            } else {
-                cur = stack[--sp];
-            }
-        }
+        while (cur >= 0) cur = node_step(sc, cur, s, tmin_f, tmax_f, stack, sp, tally);
         if (cur == kSentinel) break;
         if (cur == kLeaveInstance) {
-            make_space(ray.o, ray.d, s);
+            make_slab(ray.o, ray.d, s);
+            o = ray.o; d = ray.d;
             cur_chain = 0;
             cur = stack[--sp];
             continue;
         }
-        // ---- leaf ----
         int32_t v = ~cur;
         int32_t first = v >> 4, count = v & 15;
         cur = stack[--sp];
         for (int32_t i = 0; i < count; ++i) {
             const Record* rp = sc.records + first + i;
             int4 h = __ldg(reinterpret_cast<const int4*>(rp));
-            const double* d = rp->d;
-            double t;
-            bool hit = false;
-            if (h.x == REC_SPHERE) {
-                tally.sphere();
-                double2 a = __ldg(reinterpret_cast<const double2*>(d)), b = __ldg(reinterpret_cast<const double2*>(d + 2));
-                hit = sphere_roots(s, mk(a.x, a.y, b.x), b.y, tmin, best.t, t);
-            } else if (h.x == REC_MSPHERE) {
-                tally.sphere();
-                double dd[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) dd[k] = ldg_d(d + k);
-                hit = sphere_roots(s, msphere_center(dd, ray.time), dd[6], tmin, best.t, t);
-            } else if (h.x <= REC_RECT_YZ) {
-                tally.rect();
-                double dd[5];
-                double2 a = __ldg(reinterpret_cast<const double2*>(d)), b = __ldg(reinterpret_cast<const double2*>(d + 2));
-                dd[0] = a.x; dd[1] = a.y; dd[2] = b.x; dd[3] = b.y; dd[4] = ldg_d(d + 4);
-                hit = rect_hit(s, h.x - REC_RECT_XY, dd, tmin, best.t, t);
-            } else if (h.x == REC_INSTANCE) {
-                // enter the instance: re-express the ray (Translate/YRotate::hit), keep traversing in the same loop
+            if (h.x == REC_INSTANCE) {  // enter: re-express the ray (Translate/YRotate::hit), keep traversing in the same loop
                 tally.instance();
-                d3 o = ray.o, dir = ray.d;
-                for (int32_t k = 0; k < h.z; ++k) {
-                    XformOp op = sc.xforms[h.w + k];
-                    apply_op(op, o, dir);
-                }
-                make_space(o, dir, s);
                 cur_chain = h.w | (h.z << 24);
+                o = ray.o; d = ray.d;
+                to_space(sc, cur_chain, o, d);
+                make_slab(o, d, s);
                 stack[sp++] = cur;  // what we were about to visit next, resumed after the instance
                 stack[sp++] = kLeaveInstance;
                 cur = h.y;
-            } else if (kMedia) {  // REC_MEDIUM: ConstantMedium::hit, hittable.rs:740-796 (Q16)
-                tally.medium();
-                double r1, r2;
-                bool ok;
-                if (h.w < 0) {
-                    // boundary = one untransformed sphere: hit(-inf, inf) is the near root, hit(t1 + 1e-4, inf) the far
-                    // root if it clears t1 + 1e-4 (Sphere::hit tries the near root first; it is below the new t_min)
-                    d3 c = mk(ldg_d(d + 4), ldg_d(d + 5), ldg_d(d + 6));
-                    double rad = ldg_d(d + 7);
-                    d3 oc = ray.o - c;
-                    double a = dot(ray.d, ray.d), half_b = dot(oc, ray.d), cc = dot(oc, oc) - rad * rad;
-                    double disc = half_b * half_b - a * cc;
-                    ok = !(disc < 0.0);
-                    double sq = sqrt(disc);
-                    double inv_a = 1.0 / a;
-                    r1 = (-half_b - sq) * inv_a;
-                    r2 = (-half_b + sq) * inv_a;
-                    ok = ok && !(r2 < r1 + 0.0001);
-                } else {
-                    Best b1{CUDART_INF, -1, 0};
-                    traverse<false, kPrecise, kCount>(sc, h.w, ray, -CUDART_INF, b1, stack, sp, 0.0, nullptr, tally);
-                    ok = b1.rec >= 0;
-                    r1 = b1.t;
-                    if (ok) {
-                        Best b2{CUDART_INF, -1, 0};
-                        traverse<false, kPrecise, kCount>(sc, h.w, ray, r1 + 0.0001, b2, stack, sp, 0.0, nullptr, tally);
-                        ok = b2.rec >= 0;
-                        r2 = b2.t;
-                    }
+            } else if (h.x <= REC_RECT_YZ) {
+                double t;
+                if (test_geometry(rp, h.x, o, d, ray.time, tmin, best.t, t, tally)) {
+                    best.t = t;
+                    best.rec = first + i;
+                    best.chain = cur_chain;
+                    tmax_f = __double2float_ru(t);
                 }
-                if (ok) {
-                    r1 = fmax(r1, tmin);
-                    r2 = fmin(r2, best.t);
-                    if (r1 < r2) {
-                        r1 = fmax(r1, 0.0);
-                        double len = sqrt(dot(ray.d, ray.d));
-                        double inside = (r2 - r1) * len;
-                        int32_t ord = (int32_t)ldg_d(d + 1);
-                        double hit_distance;
-                        if (smp) {
-                            uint4 w = smp->block(P_MEDIUM, (uint32_t)ord >> 2);
-                            uint32_t word = (ord & 3) == 0 ? w.x : ((ord & 3) == 1 ? w.y : ((ord & 3) == 2 ? w.z : w.w));
-                            hit_distance = kPrecise ? ldg_d(d) * log(u01d(word)) : ldg_d(d) * (double)logf(u01f(word));
-                        } else {
-                            hit_distance = ldg_d(d) * log(medium_xi);
-                        }
-                        if (!(hit_distance > inside)) {
-                            t = r1 + hit_distance / len;
-                            hit = true;
-                        }
-                    }
-                }
-            }
-            if (hit) {
-                best.t = t;
-                best.rec = first + i;
-                best.chain = (h.x == REC_MEDIUM) ? 0 : cur_chain;
-                tmax_f = __double2float_ru(t);
             }
         }
     }
-    (void)sp0;
+}
+
+// ConstantMedium::hit, hittable.rs:740-796 (Q16), for the medium record `ri`: the scatter distance as
+// a candidate in [tmin, tmax]. `u` is the uniform variate the reference draws at :765.
+template <bool kPrecise, bool kCount>
+__device__ __forceinline__ bool medium_candidate(const SceneView& sc, int32_t ri, const RayD& ray, double tmin, double tmax, double u,
+                                                 int32_t* stack, double& t, Tally<kCount>& tally) {
+    const Record* rp = sc.records + ri;
+    int4 h = __ldg(reinterpret_cast<const int4*>(rp));
+    const double* q = rp->d;
+    tally.medium();
+    double r1, r2;
+    if (h.w < 0) {
+        // boundary = one untransformed sphere: hit(-inf, inf) is the near root, hit(t1 + 1e-4, inf) the far
+        // root if it clears t1 + 1e-4 (Sphere::hit tries the near root first; it is below the new t_min)
+        d3 c = mk(ldg_d(q + 4), ldg_d(q + 5), ldg_d(q + 6));
+        double rad = ldg_d(q + 7);
+        d3 oc = ray.o - c;
+        double a = dot(ray.d, ray.d), half_b = dot(oc, ray.d), cc = dot(oc, oc) - rad * rad;
+        double disc = half_b * half_b - a * cc;
+        if (disc < 0.0) return false;
+        double sq = sqrt(disc);
+        double inv_a = 1.0 / a;
+        r1 = (-half_b - sq) * inv_a;
+        r2 = (-half_b + sq) * inv_a;
+        if (r2 < r1 + 0.0001) return false;
+    } else {
+        Best b1{CUDART_INF, -1, 0};
+        traverse_simple(sc, h.w, ray, -CUDART_INF, b1, stack, 0, tally);
+        if (b1.rec < 0) return false;
+        r1 = b1.t;
+        Best b2{CUDART_INF, -1, 0};
+        traverse_simple(sc, h.w, ray, r1 + 0.0001, b2, stack, 0, tally);
+        if (b2.rec < 0) return false;
+        r2 = b2.t;
+    }
+    r1 = fmax(r1, tmin);
+    r2 = fmin(r2, tmax);
+    if (!(r1 < r2)) return false;
+    r1 = fmax(r1, 0.0);
+    double len = sqrt(dot(ray.d, ray.d));
+    double inside = (r2 - r1) * len;
+    double hit_distance = kPrecise ? ldg_d(q) * log(u) : ldg_d(q) * (double)logf((float)u);
+    if (hit_distance > inside) return false;
+    t = r1 + hit_distance / len;
+    return true;
+}
+
+// Every medium the ray can reach, before the surface traversal: the scatter point is a candidate
+// like any surface hit and the closest candidate wins — the same answer the reference's
+// `closest`-clipped ConstantMedium::hit gives in whatever order List::hit meets it. `smp` != null:
+// medium number k draws word (k & 3) of Philox block (MEDIUM, k >> 2); else `xi` is the variate.
+template <bool kPrecise, bool kCount>
+__device__ __forceinline__ void media_prepass(const SceneView& sc, const RayD& ray, const SlabRay& s, double tmin, Best& best,
+                                              double xi, const Sampler* smp, int32_t* stack, Tally<kCount>& tally) {
+    float tmin_f = __double2float_rd(tmin);
+    uint4 w = make_uint4(0, 0, 0, 0);
+    int32_t w_block = -1;
+    for (int32_t m = 0; m < sc.n_media; ++m) {
+        const float4* mp = reinterpret_cast<const float4*>(sc.media + m);
+        float4 lo = __ldg(mp), hi = __ldg(mp + 1);
+        float tn;
+        // the medium's segment is clipped to [tmin, best.t] (hittable.rs:754-761): its box bounds the segment
+        if (!slab(s, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, tmin_f, __double2float_ru(best.t), tn)) continue;
+        int32_t ri = __float_as_int(lo.w);
+        double u = xi;
+        if (smp) {
+            int32_t ord = (int32_t)ldg_d(sc.records[ri].d + 1);
+            if ((ord >> 2) != w_block) {
+                w_block = ord >> 2;
+                w = smp->block(P_MEDIUM, (uint32_t)w_block);
+            }
+            uint32_t word = (ord & 3) == 0 ? w.x : ((ord & 3) == 1 ? w.y : ((ord & 3) == 2 ? w.z : w.w));
+            u = u01d(word);
+        }
+        double t;
+        if (medium_candidate<kPrecise>(sc, ri, ray, tmin, best.t, u, stack, t, tally)) {
+            best.t = t;
+            best.rec = ri;
+            best.chain = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -464,7 +496,10 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(SceneView sc, int64_t n
         RayD ray{mk(a.x, a.y, b.x), mk(b.y, c.x, c.y), d.x};
         double tmin = d.y, tmax = e.x, xi = e.y;
         Best best{tmax, -1, 0};
-        traverse<true, true, kCount>(sc, sc.world_root, ray, tmin, best, stack, 0, xi, nullptr, tally);
+        SlabRay sr;
+        make_slab(ray.o, ray.d, sr);
+        media_prepass<true>(sc, ray, sr, tmin, best, xi, nullptr, stack, tally);
+        traverse_simple(sc, sc.world_root, ray, tmin, best, stack, 0, tally);
         if (!kCount) {
             rtx_hit h;
             if (best.rec >= 0) {
@@ -588,180 +623,314 @@ struct RenderArgs {
     int32_t width, height, spp_begin, spp_count, max_depth;
     uint32_t k0, k1;
     int32_t tiles_x, tiles_y;
+    // phase scheduling weights (see render_kernel): a phase runs when weight * lanes waiting for it is the largest
+    int32_t w_node, w_leaf, w_shade;
 };
 
-constexpr int kTileW = 8, kTileH = 4;  // one warp = one 8x4 pixel tile
+constexpr int kTileW = 8, kTileH = 4;  // work tile = 8x4 pixels x spp_count samples
+constexpr int kRenderBlock = 128;
+
+enum LaneState : int32_t {
+    ST_NEW = 0,    // needs a path sample from the pool
+    ST_TRAV = 1,   // has a ray in flight
+    ST_SHADE = 2,  // closest hit known, waiting for the shade phase
+    ST_DONE = 3    // pool empty, nothing left for this lane
+};
 
 // ---------------------------------------------------------------------------
-// K2: the path loop. One warp owns one tile at a time (dynamic fetch); each lane owns one
-// pixel and runs its samples back to back, starting its next path as soon as the current
-// one ends, so lanes at different bounce depths still execute the same traversal code.
+// K2: the path loop (render()'s pixel loop + color(), main.rs:26-45,202-217).
+//
+// A warp is the scheduling unit. Its 32 lanes each carry one path; a lane that finishes a path
+// takes the next (pixel, sample) item from the warp's pool (an 8x4 pixel tile x spp_count
+// samples, refilled from a global tile counter), so no lane waits for a neighbour's longer
+// path. The work of a path step comes in three kinds with very different code — BVH node steps
+// (fp32), leaf events (f64 primitive tests, entering / leaving an instance) and shading (hit
+// record, material, texture, Philox, next ray, medium pre-pass) — and lanes reach them at
+// different times. Instead of letting every lane run its own branch (the first version of this
+// kernel: 7 of 32 lanes active on average), the warp votes each iteration and runs ONE phase for
+// all lanes that are waiting for it: the phase with the most (weighted) waiting lanes. Lanes that
+// reach a leaf keep traversing speculatively with the leaf postponed (they block on the second).
 // ---------------------------------------------------------------------------
 template <bool kCount>
-__global__ void __launch_bounds__(128) render_kernel(RenderArgs a, float4* __restrict__ accum, unsigned long long* ray_count,
-                                                     unsigned int* work_counter, Counters* counters) {
+__global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, float4* __restrict__ accum, unsigned long long* ray_count,
+                                                              unsigned int* work_counter, Counters* counters) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     int32_t stack[kStackSize];
     Tally<kCount> tally;
-    const int n_tiles = a.tiles_x * a.tiles_y;
+    const uint32_t n_tiles = (uint32_t)(a.tiles_x * a.tiles_y);
+    const float tmin_f = __double2float_rd(0.001);
+    // the warp's pool of path samples (warp-uniform)
+    uint32_t pool_next = 0, pool_end = 0;
+    int pool_x0 = 0, pool_y0 = 0;
+    bool pool_dry = false;
+    // lane state
+    int32_t st = ST_NEW;
+    RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
+    SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Best best{0.0, -1, 0};
+    float tmax_f = 0.f;
+    int32_t cur = kSentinel, pending = 0, cur_chain = 0;  // pending: a postponed leaf (leaf codes are negative; 0 = none)
+    int sp = 0;
+    Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
+    float thr_r = 1.f, thr_g = 1.f, thr_b = 1.f, rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
+    int bounce = 0;
     unsigned long long my_rays = 0;
+
     while (true) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(work_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= (unsigned int)n_tiles) break;
-        int tx = (int)(tile % (unsigned int)a.tiles_x), ty = (int)(tile / (unsigned int)a.tiles_x);
-        int px = tx * kTileW + (lane & (kTileW - 1)), row = ty * kTileH + (lane / kTileW);  // row 0 = top
-        bool active = px < a.width && row < a.height;
-        int jrow = a.height - 1 - row;  // main.rs:202-204: j runs height-1 .. 0, top row first
-        Sampler smp{a.k0, a.k1, (uint32_t)(row * a.width + px), 0u, 0u};
-        float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f;
-        int s_idx = 0;
-        bool need_new = true;
-        RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
-        float thr_r = 1.f, thr_g = 1.f, thr_b = 1.f, rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
-        int bounce = 0;
-        bool done = !active;
-        while (!__all_sync(0xffffffffu, done)) {
-            if (done) continue;
-            if (need_new) {
-                if (s_idx >= a.spp_count) {
-                    done = true;
-                    continue;
-                }
-                // one path sample: pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25)
-                smp.sample = (uint32_t)(a.spp_begin + s_idx);
-                smp.bounce = 0;
-                uint4 w = smp.block(P_CAMERA, 0);
-                double su = ((double)px + u01d(w.x)) / (double)a.width;
-                double sv = ((double)jrow + u01d(w.y)) / (double)a.height;
-                double lx = 0.0, ly = 0.0;
-                if (a.cam.lens_radius != 0.0) {  // the draw is skipped for a pinhole: counters make that invisible
-                    for (uint32_t j = 0;; ++j) {
-                        uint4 l = smp.block(P_LENS, j);
-                        lx = 2.0 * u01d(l.x) - 1.0; ly = 2.0 * u01d(l.y) - 1.0;
-                        if (lx * lx + ly * ly < 1.0) break;
-                        lx = 2.0 * u01d(l.z) - 1.0; ly = 2.0 * u01d(l.w) - 1.0;
-                        if (lx * lx + ly * ly < 1.0) break;
-                    }
-                }
-                double rdx = a.cam.lens_radius * lx, rdy = a.cam.lens_radius * ly;
-                d3 off = mk(a.cam.u[0] * rdx + a.cam.v[0] * rdy, a.cam.u[1] * rdx + a.cam.v[1] * rdy, a.cam.u[2] * rdx + a.cam.v[2] * rdy);
-                ray.o = mk(a.cam.origin[0] + off.x, a.cam.origin[1] + off.y, a.cam.origin[2] + off.z);
-                ray.d = mk(a.cam.lower_left[0] + su * a.cam.horizontal[0] + sv * a.cam.vertical[0] - a.cam.origin[0] - off.x,
-                           a.cam.lower_left[1] + su * a.cam.horizontal[1] + sv * a.cam.vertical[1] - a.cam.origin[1] - off.y,
-                           a.cam.lower_left[2] + su * a.cam.horizontal[2] + sv * a.cam.vertical[2] - a.cam.origin[2] - off.z);
-                ray.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01d(w.z);
-                thr_r = thr_g = thr_b = 1.f;
-                rad_r = rad_g = rad_b = 0.f;
-                bounce = 0;
-                need_new = false;
-            }
-            // ---- color(), main.rs:26-45, one level per iteration (Q7) ----
-            smp.bounce = (uint32_t)bounce;
-            Best best{1.7976931348623157e308, -1, 0};
-            traverse<true, false, kCount>(a.sc, a.sc.world_root, ray, 0.001, best, stack, 0, 0.0, &smp, tally);
-            ++my_rays;
-            bool end_path = false;
-            if (best.rec < 0) {  // background (Q8)
-                rad_r += thr_r * a.cam.background[0]; rad_g += thr_g * a.cam.background[1]; rad_b += thr_b * a.cam.background[2];
-                end_path = true;
-            } else {
-                HitOut ho;
-                finalize_hit<false>(a.sc, ray, best, ho);
-                int32_t mkind, mtex;
-                float alb_r = 0.f, alb_g = 0.f, alb_b = 0.f, mparam = 0.f;
-                if (ho.material < 0) {  // ConstantMedium's own Isotropic (hittable.rs:726,786)
-                    mkind = RTX_MAT_ISOTROPIC;
-                    mtex = -(ho.material + 1);
-                } else {
-                    DMaterial m = a.sc.materials[ho.material];
-                    mkind = m.kind; mtex = m.texture; alb_r = m.albedo[0]; alb_g = m.albedo[1]; alb_b = m.albedo[2]; mparam = m.param;
-                }
-                float tu = (float)ho.u, tv = (float)ho.v;
-                if (mtex >= 0 && ho.type == REC_SPHERE && a.sc.textures[mtex]._pad) {
-                    // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
-                    const float PI = 3.14159265358979f;
-                    tv = acosf(-(float)ho.on.y) / PI;
-                    tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
-                }
-                d3 udir;
-                if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
-                    f3 e = texture_value(a.sc, mtex, tu, tv, ho.p);
-                    rad_r += thr_r * e.x; rad_g += thr_g * e.y; rad_b += thr_b * e.z;
-                    end_path = true;
-                } else if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
-                    d3 b = random_in_unit_space(smp);
-                    ray.d = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
-                    f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
-                    thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
-                } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
-                    ray.d = random_in_unit_space(smp);
-                    f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
-                    thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
-                } else if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
-                    double k = 1.0 / sqrt(dot(ray.d, ray.d));
-                    udir = k * ray.d;
-                    d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
-                    d3 b = random_in_unit_space(smp);
-                    d3 nd = refl + (double)mparam * b;
-                    if (dot(nd, ho.n) > 0.0) {
-                        ray.d = nd;
-                        thr_r *= alb_r; thr_g *= alb_g; thr_b *= alb_b;
-                    } else {
-                        end_path = true;  // absorbed: only `emitted` (= 0) is returned
-                    }
-                } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
-                    double ir = (double)mparam;
-                    double ratio = ho.front_face ? 1.0 / ir : ir;
-                    double k = 1.0 / sqrt(dot(ray.d, ray.d));
-                    udir = k * ray.d;
-                    double cos_theta = fmin(dot(-udir, ho.n), 1.0);
-                    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
-                    bool reflect = ratio * sin_theta > 1.0;
-                    if (!reflect) {
-                        double r0 = (1.0 - ratio) / (1.0 + ratio);
-                        r0 = r0 * r0;
-                        double om = 1.0 - cos_theta;
-                        double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
-                        uint4 w = smp.block(P_SCATTER, 0);
-                        reflect = schlick > u01d(w.w);
-                    }
-                    if (reflect) {
-                        ray.d = udir - (2.0 * dot(udir, ho.n)) * ho.n;
-                    } else {  // vec3.rs:116-121
-                        d3 perp = ratio * (udir + cos_theta * ho.n);
-                        d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
-                        ray.d = perp + par;
-                    }
-                }
-                ray.o = ho.p;
-                ++bounce;
-                if (bounce >= a.max_depth) end_path = true;  // color(depth = 0) returns 0
-            }
-            if (end_path) {
-                sum_r += rad_r; sum_g += rad_g; sum_b += rad_b;
-                ++s_idx;
-                need_new = true;
+        // ---- cheap per-lane transitions, then the vote ----
+        if (st == ST_TRAV && cur < 0) {
+            if (cur == kSentinel) {
+                if (pending == 0) st = ST_SHADE;
+            } else if (cur != kLeaveInstance && pending == 0) {
+                pending = cur;  // postpone the leaf, keep traversing (speculatively: best.t is not shrunk yet)
+                cur = stack[--sp];
             }
         }
-        if (active) {
-            float* dst = reinterpret_cast<float*>(accum + (size_t)row * a.width + px);
-            atomicAdd(dst + 0, sum_r);
-            atomicAdd(dst + 1, sum_g);
-            atomicAdd(dst + 2, sum_b);
-            atomicAdd(dst + 3, (float)a.spp_count);
+        const bool want_node = st == ST_TRAV && cur >= 0;
+        const bool want_leaf = st == ST_TRAV && cur < 0 && (pending != 0 || cur == kLeaveInstance);
+        const bool want_shade = st == ST_SHADE || st == ST_NEW;
+        const int n_node = __popc(__ballot_sync(FULL, want_node));
+        const int n_leaf = __popc(__ballot_sync(FULL, want_leaf));
+        const int n_shade = __popc(__ballot_sync(FULL, want_shade));
+        if ((n_node | n_leaf | n_shade) == 0) {
+            // lanes that popped a leaf / sentinel this very iteration settle on the next one; only ST_DONE ends the loop
+            if (__all_sync(FULL, st == ST_DONE)) break;
+            continue;
+        }
+        const int s_node = n_node * a.w_node, s_leaf = n_leaf * a.w_leaf, s_shade = n_shade * a.w_shade;
+
+        if (s_node >= s_leaf && s_node >= s_shade) {
+            // ================= node phase =================
+            if (want_node) cur = node_step(a.sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
+        } else if (s_leaf >= s_shade) {
+            // ================= leaf phase =================
+            if (want_leaf) {
+                if (pending != 0) {
+                    d3 o = ray.o, d = ray.d;
+                    if (cur_chain != 0) to_space(a.sc, cur_chain, o, d);
+                    int32_t v = ~pending;
+                    int32_t first = v >> 4, count = v & 15;
+                    pending = 0;
+                    for (int32_t i = 0; i < count; ++i) {
+                        const Record* rp = a.sc.records + first + i;
+                        int4 h = __ldg(reinterpret_cast<const int4*>(rp));
+                        if (h.x == REC_INSTANCE) {  // Translate / YRotate::hit: re-express the ray, descend
+                            tally.instance();
+                            cur_chain = h.w | (h.z << 24);
+                            o = ray.o; d = ray.d;
+                            to_space(a.sc, cur_chain, o, d);
+                            make_slab(o, d, sr);
+                            stack[sp++] = cur;
+                            stack[sp++] = kLeaveInstance;
+                            cur = h.y;
+                        } else if (h.x <= REC_RECT_YZ) {
+                            double t;
+                            if (test_geometry(rp, h.x, o, d, ray.time, 0.001, best.t, t, tally)) {
+                                best.t = t;
+                                best.rec = first + i;
+                                best.chain = cur_chain;
+                                tmax_f = __double2float_ru(t);
+                            }
+                        }
+                    }
+                }
+                if (cur == kLeaveInstance) {  // back to world space
+                    make_slab(ray.o, ray.d, sr);
+                    cur_chain = 0;
+                    cur = stack[--sp];
+                }
+            }
+        } else {
+            // ================= shade phase =================
+            bool fresh = false;  // this lane leaves the phase with a new ray to trace
+            if (st == ST_SHADE) {
+                // ---- color(), main.rs:26-45, one level (Q7) ----
+                bool end_path = false;
+                if (best.rec < 0) {  // background (Q8)
+                    rad_r += thr_r * a.cam.background[0]; rad_g += thr_g * a.cam.background[1]; rad_b += thr_b * a.cam.background[2];
+                    end_path = true;
+                } else {
+                    HitOut ho;
+                    finalize_hit<false>(a.sc, ray, best, ho);
+                    int32_t mkind, mtex;
+                    float alb_r = 0.f, alb_g = 0.f, alb_b = 0.f, mparam = 0.f;
+                    if (ho.material < 0) {  // ConstantMedium's own Isotropic (hittable.rs:726,786)
+                        mkind = RTX_MAT_ISOTROPIC;
+                        mtex = -(ho.material + 1);
+                    } else {
+                        DMaterial m = a.sc.materials[ho.material];
+                        mkind = m.kind; mtex = m.texture; alb_r = m.albedo[0]; alb_g = m.albedo[1]; alb_b = m.albedo[2]; mparam = m.param;
+                    }
+                    float tu = (float)ho.u, tv = (float)ho.v;
+                    if (mtex >= 0 && ho.type == REC_SPHERE && a.sc.textures[mtex]._pad) {
+                        // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
+                        const float PI = 3.14159265358979f;
+                        tv = acosf(-(float)ho.on.y) / PI;
+                        tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+                    }
+                    d3 udir;
+                    if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
+                        f3 e = texture_value(a.sc, mtex, tu, tv, ho.p);
+                        rad_r += thr_r * e.x; rad_g += thr_g * e.y; rad_b += thr_b * e.z;
+                        end_path = true;
+                    } else if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
+                        d3 b = random_in_unit_space(smp);
+                        ray.d = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
+                        f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
+                        thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
+                    } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
+                        ray.d = random_in_unit_space(smp);
+                        f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
+                        thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
+                    } else if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
+                        double k = 1.0 / sqrt(dot(ray.d, ray.d));
+                        udir = k * ray.d;
+                        d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
+                        d3 b = random_in_unit_space(smp);
+                        d3 nd = refl + (double)mparam * b;
+                        if (dot(nd, ho.n) > 0.0) {
+                            ray.d = nd;
+                            thr_r *= alb_r; thr_g *= alb_g; thr_b *= alb_b;
+                        } else {
+                            end_path = true;  // absorbed: only `emitted` (= 0) is returned
+                        }
+                    } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
+                        double ir = (double)mparam;
+                        double ratio = ho.front_face ? 1.0 / ir : ir;
+                        double k = 1.0 / sqrt(dot(ray.d, ray.d));
+                        udir = k * ray.d;
+                        double cos_theta = fmin(dot(-udir, ho.n), 1.0);
+                        double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+                        bool reflect = ratio * sin_theta > 1.0;
+                        if (!reflect) {
+                            double r0 = (1.0 - ratio) / (1.0 + ratio);
+                            r0 = r0 * r0;
+                            double om = 1.0 - cos_theta;
+                            double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
+                            uint4 w = smp.block(P_SCATTER, 0);
+                            reflect = schlick > u01d(w.w);
+                        }
+                        if (reflect) {
+                            ray.d = udir - (2.0 * dot(udir, ho.n)) * ho.n;
+                        } else {  // vec3.rs:116-121
+                            d3 perp = ratio * (udir + cos_theta * ho.n);
+                            d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
+                            ray.d = perp + par;
+                        }
+                    }
+                    ray.o = ho.p;
+                    ++bounce;
+                    if (bounce >= a.max_depth) end_path = true;  // color(depth = 0) returns 0
+                }
+                if (end_path) {
+                    // one path sample done: add it to its pixel (sum r, g, b, count)
+                    atomicAdd(accum + smp.pixel, make_float4(rad_r, rad_g, rad_b, 1.0f));
+                    st = ST_NEW;
+                } else {
+                    fresh = true;
+                }
+            }
+            // ---- hand out path samples to the lanes that need one ----
+            uint32_t need = __ballot_sync(FULL, st == ST_NEW);
+            while (need != 0) {
+                if (pool_next >= pool_end) {  // warp-uniform: refill from the global tile counter
+                    if (!pool_dry) {
+                        unsigned int tile = 0;
+                        if (lane == 0) tile = atomicAdd(work_counter, 1u);
+                        tile = __shfl_sync(FULL, tile, 0);
+                        if (tile < n_tiles) {
+                            pool_x0 = (int)(tile % (unsigned int)a.tiles_x) * kTileW;
+                            pool_y0 = (int)(tile / (unsigned int)a.tiles_x) * kTileH;
+                            pool_next = 0;
+                            pool_end = 32u * (uint32_t)a.spp_count;
+                        } else {
+                            pool_dry = true;
+                        }
+                    }
+                    if (pool_dry) {
+                        if (st == ST_NEW) st = ST_DONE;
+                        break;
+                    }
+                }
+                const uint32_t avail = pool_end - pool_next;
+                const uint32_t rank = (uint32_t)__popc(need & lt_mask);
+                const bool take = ((need >> lane) & 1u) != 0 && rank < avail;
+                if (take) {
+                    // item -> (sample, pixel of the tile): consecutive items are the 32 pixels of one sample index
+                    const uint32_t item = pool_next + rank;
+                    const int pi = (int)(item & 31u);
+                    const int px = pool_x0 + (pi & (kTileW - 1)), row = pool_y0 + (pi / kTileW);  // row 0 = top
+                    if (px < a.width && row < a.height) {
+                        const int jrow = a.height - 1 - row;  // main.rs:202-204: j runs height-1 .. 0, top row first
+                        smp.pixel = (uint32_t)(row * a.width + px);
+                        smp.sample = (uint32_t)a.spp_begin + (item >> 5);
+                        smp.bounce = 0;
+                        if (a.max_depth <= 0) {  // color(.., depth = 0) is black without tracing anything (main.rs:27-29)
+                            atomicAdd(accum + smp.pixel, make_float4(0.f, 0.f, 0.f, 1.0f));
+                        } else {
+                            // pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25)
+                            uint4 w = smp.block(P_CAMERA, 0);
+                            double su = ((double)px + u01d(w.x)) / (double)a.width;
+                            double sv = ((double)jrow + u01d(w.y)) / (double)a.height;
+                            double lx = 0.0, ly = 0.0;
+                            if (a.cam.lens_radius != 0.0) {  // the draw is skipped for a pinhole: counters make that invisible
+                                for (uint32_t j = 0;; ++j) {
+                                    uint4 l = smp.block(P_LENS, j);
+                                    lx = 2.0 * u01d(l.x) - 1.0; ly = 2.0 * u01d(l.y) - 1.0;
+                                    if (lx * lx + ly * ly < 1.0) break;
+                                    lx = 2.0 * u01d(l.z) - 1.0; ly = 2.0 * u01d(l.w) - 1.0;
+                                    if (lx * lx + ly * ly < 1.0) break;
+                                }
+                            }
+                            double rdx = a.cam.lens_radius * lx, rdy = a.cam.lens_radius * ly;
+                            d3 off = mk(a.cam.u[0] * rdx + a.cam.v[0] * rdy, a.cam.u[1] * rdx + a.cam.v[1] * rdy, a.cam.u[2] * rdx + a.cam.v[2] * rdy);
+                            ray.o = mk(a.cam.origin[0] + off.x, a.cam.origin[1] + off.y, a.cam.origin[2] + off.z);
+                            ray.d = mk(a.cam.lower_left[0] + su * a.cam.horizontal[0] + sv * a.cam.vertical[0] - a.cam.origin[0] - off.x,
+                                       a.cam.lower_left[1] + su * a.cam.horizontal[1] + sv * a.cam.vertical[1] - a.cam.origin[1] - off.y,
+                                       a.cam.lower_left[2] + su * a.cam.horizontal[2] + sv * a.cam.vertical[2] - a.cam.origin[2] - off.z);
+                            ray.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01d(w.z);
+                            thr_r = thr_g = thr_b = 1.f;
+                            rad_r = rad_g = rad_b = 0.f;
+                            bounce = 0;
+                            fresh = true;
+                            st = ST_TRAV;
+                        }
+                    }
+                    // (a pixel outside a ragged image edge, or depth 0: the lane stays ST_NEW and takes another item)
+                }
+                pool_next += min((uint32_t)__popc(need), avail);
+                need = __ballot_sync(FULL, st == ST_NEW);
+            }
+            // ---- new rays: media first, then the surface traversal starts at the world root ----
+            if (fresh) {
+                smp.bounce = (uint32_t)bounce;
+                best.t = 1.7976931348623157e308;
+                best.rec = -1;
+                best.chain = 0;
+                make_slab(ray.o, ray.d, sr);
+                if (a.sc.n_media > 0) media_prepass<false>(a.sc, ray, sr, 0.001, best, 0.0, &smp, stack, tally);
+                tmax_f = __double2float_ru(best.t);
+                sp = 0;
+                stack[sp++] = kSentinel;
+                cur = a.sc.world_root;
+                pending = 0;
+                cur_chain = 0;
+                st = ST_TRAV;
+                ++my_rays;
+            }
         }
     }
     if (ray_count) {
-        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, off);
+        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(FULL, my_rays, off);
         if (lane == 0 && my_rays) atomicAdd(ray_count, my_rays);
     }
     if constexpr (kCount) {
         uint32_t vals[5] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst, tally.n_med};
 #pragma unroll
         for (int k = 0; k < 5; ++k)
-            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], off);
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
         if (lane == 0) {
             atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
             atomicAdd(&counters->box_tests, 2ull * vals[0]);
