@@ -41,6 +41,7 @@ struct rtx_ctx {
     int sm_count = 0;
     unsigned int* d_work_counter = nullptr;  // render_kernel's tile dispenser
     rtx::Counters* d_counters = nullptr;
+    int node_burst = 4;
     int w_node = 1, w_leaf = 1, w_shade = 1;  // render_kernel phase weights (RTX_W_NODE / RTX_W_LEAF / RTX_W_SHADE override)
 };
 
@@ -99,6 +100,7 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->w_node = env_int("RTX_W_NODE", c->w_node);
     c->w_leaf = env_int("RTX_W_LEAF", c->w_leaf);
     c->w_shade = env_int("RTX_W_SHADE", c->w_shade);
+    c->node_burst = env_int("RTX_NODE_BURST", c->node_burst);
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -175,7 +177,8 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     size_t off_nodes = 0;
     size_t off_records = align(off_nodes + fs.nodes.size() * sizeof(rtx::BvhNode));
     size_t off_xforms = align(off_records + fs.records.size() * sizeof(rtx::Record));
-    size_t off_mats = align(off_xforms + fs.xforms.size() * sizeof(rtx::XformOp));
+    size_t off_chains = align(off_xforms + fs.xforms.size() * sizeof(rtx::XformOp));
+    size_t off_mats = align(off_chains + fs.chains.size() * sizeof(rtx::DChain));
     size_t off_texs = align(off_mats + fs.materials.size() * sizeof(rtx::DMaterial));
     size_t off_perlins = align(off_texs + fs.textures.size() * sizeof(rtx::DTexture));
     size_t off_images = align(off_perlins + fs.perlins.size() * sizeof(rtx::DPerlin));
@@ -186,6 +189,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     put(off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(rtx::BvhNode));
     put(off_records, fs.records.data(), fs.records.size() * sizeof(rtx::Record));
     put(off_xforms, fs.xforms.data(), fs.xforms.size() * sizeof(rtx::XformOp));
+    put(off_chains, fs.chains.data(), fs.chains.size() * sizeof(rtx::DChain));
     put(off_mats, fs.materials.data(), fs.materials.size() * sizeof(rtx::DMaterial));
     put(off_texs, fs.textures.data(), fs.textures.size() * sizeof(rtx::DTexture));
     put(off_perlins, fs.perlins.data(), fs.perlins.size() * sizeof(rtx::DPerlin));
@@ -201,6 +205,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->view.nodes = (const rtx::BvhNode*)(base + off_nodes);
     s->view.records = (const rtx::Record*)(base + off_records);
     s->view.xforms = (const rtx::XformOp*)(base + off_xforms);
+    s->view.chains = (const rtx::DChain*)(base + off_chains);
     s->view.materials = (const rtx::DMaterial*)(base + off_mats);
     s->view.textures = (const rtx::DTexture*)(base + off_texs);
     s->view.perlins = (const rtx::DPerlin*)(base + off_perlins);
@@ -316,6 +321,7 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     a.tiles_x = (p->width + rtx::kTileW - 1) / rtx::kTileW;
     a.tiles_y = (p->height + rtx::kTileH - 1) / rtx::kTileH;
     a.w_node = c->w_node; a.w_leaf = c->w_leaf; a.w_shade = c->w_shade;
+    a.node_burst = c->node_burst;
     CU(cudaMemsetAsync(c->d_work_counter, 0, sizeof(unsigned int), c->stream));
     // persistent grid: as many CTAs as fit, a whole number per SM
     int per_sm = 0;

@@ -26,10 +26,10 @@ enum RecType : int32_t {
     REC_RECT_XY = 2,   // d = {a0, a1, b0, b1, k}  (axis0, axis1, k_axis) = (0,1,2)
     REC_RECT_XZ = 3,   //                                                   (0,2,1)
     REC_RECT_YZ = 4,   //                                                   (1,2,0)
-    REC_INSTANCE = 5,  // a = BVH root of the instanced group, b = chain length, c = chain begin
+    REC_INSTANCE = 5,  // a = BVH root of the instanced group, c = chain index (SceneView::chains)
     REC_MEDIUM = 6     // a = phase texture, b = prim id, c = boundary BVH root (or -1: the boundary is
                        // the untransformed sphere d[4..7] = {cx, cy, cz, r});
-                       // d = {neg_inv_density, medium ordinal, outer chain begin, outer chain len}.
+                       // d = {neg_inv_density, medium ordinal, outer chain index}.
                        // Medium records are not BVH leaves: they are listed in SceneView::media.
 };
 
@@ -53,6 +53,19 @@ struct alignas(16) XformOp {
     double v[3];  // TRANSLATE: offset; ROTATE_Y: {sin, cos, -}
 };
 static_assert(sizeof(XformOp) == 32, "XformOp must be 32 bytes");
+
+// One entry per distinct wrapper path. Any sequence of Translate / YRotate ops composes to a
+// rotation about y plus an offset: ray-into-object-space is o' = Ry(cs, sn) o + t, d' = Ry d (what
+// the chain of Translate::hit / YRotate::hit computes, hittable.rs:600-604,687-692, in one step).
+// The individual ops (xforms[begin .. begin + len), outermost first) are still needed on the way
+// out, where the reference post-processes the hit record op by op (Q13 / Q14). Chain 0 = identity.
+struct alignas(16) DChain {
+    double cs, sn;
+    double tx, ty, tz;
+    int32_t begin, len;
+    double _pad[2];
+};
+static_assert(sizeof(DChain) == 64, "DChain must be 64 bytes");
 
 struct alignas(16) DMaterial {
     int32_t kind;  // rtx_material_kind
@@ -99,6 +112,7 @@ struct SceneView {
     const BvhNode* nodes;
     const Record* records;
     const XformOp* xforms;
+    const DChain* chains;
     const DMaterial* materials;
     const DTexture* textures;
     const DPerlin* perlins;

@@ -411,9 +411,7 @@ struct Flattener {
                 it.rec.c = root;
                 it.rec.d[0] = -1.0 / f[0];  // ConstantMedium::new, hittable.rs:731-735
                 it.rec.d[1] = (double)medium_ord[(size_t)ni];
-                it.rec.d[2] = (double)out.xforms.size();
-                it.rec.d[3] = (double)chain.size();
-                for (const auto& op : chain) out.xforms.push_back(op);
+                it.rec.d[2] = (double)add_chain(chain);
                 it.box = bounds;
                 w.media.push_back(it);
                 return true;
@@ -421,6 +419,29 @@ struct Flattener {
             default:
                 return fail("unknown node kind");
         }
+    }
+
+    // Registers a wrapper path: its ops (for the way out) and their composition (for the way in).
+    int32_t add_chain(const std::vector<XformOp>& chain) {
+        if (chain.empty()) return 0;
+        DChain c;
+        std::memset(&c, 0, sizeof(c));
+        c.cs = 1.0;
+        c.begin = (int32_t)out.xforms.size();
+        c.len = (int32_t)chain.size();
+        for (const auto& op : chain) {  // outermost first, the order the wrappers see the ray
+            out.xforms.push_back(op);
+            if (op.kind == XF_TRANSLATE) {
+                c.tx -= op.v[0]; c.ty -= op.v[1]; c.tz -= op.v[2];
+            } else {
+                double s = op.v[0], k = op.v[1];
+                double cs = k * c.cs - s * c.sn, sn = s * c.cs + k * c.sn;
+                double tx = k * c.tx - s * c.tz, tz = s * c.tx + k * c.tz;
+                c.cs = cs; c.sn = sn; c.tx = tx; c.tz = tz;
+            }
+        }
+        out.chains.push_back(c);
+        return (int32_t)out.chains.size() - 1;
     }
 
     // object -> world: undo the chain, innermost op first
@@ -457,9 +478,7 @@ struct Flattener {
             std::memset(&inst.rec, 0, sizeof(inst.rec));
             inst.rec.type = REC_INSTANCE;
             inst.rec.a = root;
-            inst.rec.b = (int32_t)g.chain.size();
-            inst.rec.c = (int32_t)out.xforms.size();
-            for (const auto& op : g.chain) out.xforms.push_back(op);
+            inst.rec.c = add_chain(g.chain);
             inst.box.reset();
             if (!g.items.empty()) {
                 for (int corner = 0; corner < 8; ++corner) {
@@ -495,6 +514,12 @@ struct Flattener {
     bool run() {
         if (!d.nodes || d.n_nodes <= 0) return fail("scene has no nodes");
         if (d.root < 0 || d.root >= d.n_nodes) return fail("root index out of range");
+        {
+            DChain identity;
+            std::memset(&identity, 0, sizeof(identity));
+            identity.cs = 1.0;
+            out.chains.push_back(identity);
+        }
         first_id.assign((size_t)d.n_nodes, -1);
         medium_ord.assign((size_t)d.n_nodes, -1);
         t_a = std::fmin(0.0, d.camera.open_time);
@@ -681,7 +706,9 @@ struct Checker {
                     if (record_box(r, b)) {
                         if (!inside(lo, hi, b)) return fail("record not inside its leaf box");
                     } else if (r.type == REC_INSTANCE) {
-                        if (r.c < 0 || r.c + r.b > (int)fs.xforms.size()) return fail("instance chain out of range");
+                        if (r.c <= 0 || r.c >= (int)fs.chains.size()) return fail("instance chain out of range");
+                        const DChain& ch = fs.chains[(size_t)r.c];
+                        if (ch.begin < 0 || ch.len <= 0 || ch.begin + ch.len > (int)fs.xforms.size()) return fail("chain ops out of range");
                         int sub = 0;
                         if (!walk(r.a, depth + 1, sub)) return false;
                     } else {

@@ -24,6 +24,7 @@ struct FlatScene {
     std::vector<BvhNode> nodes;
     std::vector<Record> records;
     std::vector<XformOp> xforms;
+    std::vector<DChain> chains;  // chains[0] = identity
     std::vector<DMaterial> materials;
     std::vector<DTexture> textures;
     std::vector<DPerlin> perlins;

@@ -25,6 +25,8 @@ namespace rtx {
 // ---------------------------------------------------------------------------
 // small vector helpers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double ldg_d(const double* p) { return __ldg(p); }
+
 struct d3 {
     double x, y, z;
 };
@@ -147,10 +149,14 @@ __device__ __forceinline__ void apply_op(const XformOp& op, d3& o, d3& d) {
         d = mk(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z);
     }
 }
-// chain = begin | len << 24 (0 = world space)
+// The ray in the object space of chain `chain` (an index into SceneView::chains; 0 = world): the
+// composition of the wrappers' Translate::hit / YRotate::hit ray transforms, applied in one step.
 __device__ __forceinline__ void to_space(const SceneView& sc, int32_t chain, d3& o, d3& d) {
-    int32_t begin = chain & 0xFFFFFF, len = (uint32_t)chain >> 24;
-    for (int32_t k = 0; k < len; ++k) apply_op(sc.xforms[begin + k], o, d);
+    const double2* cp = reinterpret_cast<const double2*>(sc.chains + chain);
+    double2 r = __ldg(cp), t0 = __ldg(cp + 1);
+    double tz = ldg_d(&sc.chains[chain].tz);
+    o = mk(r.x * o.x - r.y * o.z + t0.x, o.y + t0.y, r.y * o.x + r.x * o.z + tz);
+    d = mk(r.x * d.x - r.y * d.z, d.y, r.y * d.x + r.x * d.z);
 }
 
 // ---------------------------------------------------------------------------
@@ -194,36 +200,34 @@ __device__ __forceinline__ bool rect_hit(d3 o, d3 d, int plane, const double* r,
 struct Best {
     double t;       // closest accepted distance so far (the `closest` of List::hit, hittable.rs:155)
     int32_t rec;    // record index, -1 = none
-    int32_t chain;  // transform chain of the instance the record was hit in: begin | len << 24
+    int32_t chain;  // transform chain of the instance the record was hit in (index into SceneView::chains)
 };
 
 constexpr int kStackSize = kTraversalStack;
 constexpr int32_t kSentinel = (int32_t)0x80000000;       // bottom of a query's stack
 constexpr int32_t kLeaveInstance = (int32_t)0x80000001;  // pop: return to the query's own space
 
-__device__ __forceinline__ double ldg_d(const double* p) { return __ldg(p); }
-
 // One geometric record (sphere / moving sphere / rectangle) against the ray (o, d) of its space.
+// One copy of each intersection routine per kernel: code size is what the instruction cache sees.
 template <bool kCount>
 __device__ __forceinline__ bool test_geometry(const Record* rp, int32_t type, d3 o, d3 d, double time, double tmin, double tmax,
                                               double& t, Tally<kCount>& tally) {
     const double* q = rp->d;
-    if (type == REC_SPHERE) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
+    if (type <= REC_MSPHERE) {
         tally.sphere();
-        double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
-        return sphere_roots(o, d, mk(a.x, a.y, b.x), b.y, tmin, tmax, t);
-    }
-    if (type == REC_MSPHERE) {
-        tally.sphere();
-        double dd[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) dd[k] = ldg_d(q + k);
-        return sphere_roots(o, d, msphere_center(dd, time), dd[6], tmin, tmax, t);
+        d3 c = mk(a.x, a.y, b.x);
+        double r = b.y;
+        if (type == REC_MSPHERE) {  // MovingSphere::center, hittable.rs:187-191
+            double2 e = __ldg(reinterpret_cast<const double2*>(q + 4)), g = __ldg(reinterpret_cast<const double2*>(q + 6));
+            double f = (time - g.y) * ldg_d(q + 8);
+            c = mk(a.x + f * b.y, a.y + f * e.x, b.x + f * e.y);
+            r = g.x;
+        }
+        return sphere_roots(o, d, c, r, tmin, tmax, t);
     }
     tally.rect();
-    double dd[5];
-    double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
-    dd[0] = a.x; dd[1] = a.y; dd[2] = b.x; dd[3] = b.y; dd[4] = ldg_d(q + 4);
+    double dd[5] = {a.x, a.y, b.x, b.y, ldg_d(q + 4)};
     return rect_hit(o, d, type - REC_RECT_XY, dd, tmin, tmax, t);
 }
 
@@ -257,19 +261,23 @@ template <bool kCount>
 __device__ __forceinline__ void traverse_simple(const SceneView& sc, int32_t root, const RayD& ray, double tmin, Best& best,
                                                 int32_t* stack, int sp, Tally<kCount>& tally) {
     SlabRay s;
-    make_slab(ray.o, ray.d, s);
     d3 o = ray.o, d = ray.d;
+    bool reslab = true;
     float tmin_f = __double2float_rd(tmin);
     float tmax_f = __double2float_ru(best.t);
     int32_t cur_chain = 0;
     stack[sp++] = kSentinel;
     int32_t cur = root;
     while (true) {
+        if (reslab) {
+            make_slab(o, d, s);
+            reslab = false;
+        }
         while (cur >= 0) cur = node_step(sc, cur, s, tmin_f, tmax_f, stack, sp, tally);
         if (cur == kSentinel) break;
         if (cur == kLeaveInstance) {
-            make_slab(ray.o, ray.d, s);
             o = ray.o; d = ray.d;
+            reslab = true;
             cur_chain = 0;
             cur = stack[--sp];
             continue;
@@ -282,10 +290,10 @@ __device__ __forceinline__ void traverse_simple(const SceneView& sc, int32_t roo
             int4 h = __ldg(reinterpret_cast<const int4*>(rp));
             if (h.x == REC_INSTANCE) {  // enter: re-express the ray (Translate/YRotate::hit), keep traversing in the same loop
                 tally.instance();
-                cur_chain = h.w | (h.z << 24);
+                cur_chain = h.w;
                 o = ray.o; d = ray.d;
                 to_space(sc, cur_chain, o, d);
-                make_slab(o, d, s);
+                reslab = true;
                 stack[sp++] = cur;  // what we were about to visit next, resumed after the instance
                 stack[sp++] = kLeaveInstance;
                 cur = h.y;
@@ -327,14 +335,16 @@ __device__ __forceinline__ bool medium_candidate(const SceneView& sc, int32_t ri
         r2 = (-half_b + sq) * inv_a;
         if (r2 < r1 + 0.0001) return false;
     } else {
-        Best b1{CUDART_INF, -1, 0};
-        traverse_simple(sc, h.w, ray, -CUDART_INF, b1, stack, 0, tally);
-        if (b1.rec < 0) return false;
-        r1 = b1.t;
-        Best b2{CUDART_INF, -1, 0};
-        traverse_simple(sc, h.w, ray, r1 + 0.0001, b2, stack, 0, tally);
-        if (b2.rec < 0) return false;
-        r2 = b2.t;
+        // boundary.hit(ray, -inf, inf) then boundary.hit(ray, t1 + 1e-4, inf), hittable.rs:745-752
+        r1 = r2 = 0.0;
+        double from = -CUDART_INF;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            Best b{CUDART_INF, -1, 0};
+            traverse_simple(sc, h.w, ray, from, b, stack, 0, tally);
+            if (b.rec < 0) return false;
+            if (pass == 0) { r1 = b.t; from = r1 + 0.0001; } else { r2 = b.t; }
+        }
     }
     r1 = fmax(r1, tmin);
     r2 = fmin(r2, tmax);
@@ -410,13 +420,15 @@ __device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ra
     const Record* rp = sc.records + best.rec;
     int4 h = __ldg(reinterpret_cast<const int4*>(rp));
     const double* d = rp->d;
-    int32_t begin = best.chain & 0xFFFFFF, len = (uint32_t)best.chain >> 24;
-    if (h.x == REC_MEDIUM) {
-        begin = (int32_t)ldg_d(d + 2);
-        len = (int32_t)ldg_d(d + 3);
-    }
+    int32_t chain = best.chain;
+    if (h.x == REC_MEDIUM) chain = (int32_t)ldg_d(d + 2);
     d3 o = ray.o, dir = ray.d;
-    for (int32_t k = 0; k < len; ++k) apply_op(sc.xforms[begin + k], o, dir);
+    int32_t begin = 0, len = 0;
+    if (chain != 0) {
+        to_space(sc, chain, o, dir);
+        begin = sc.chains[chain].begin;
+        len = sc.chains[chain].len;
+    }
     double t = best.t;
     d3 p = o + t * dir;  // Ray::point_at_parameter in the primitive's own space
     d3 n;
@@ -433,17 +445,16 @@ __device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ra
         out.material = -(1 + h.y);
     } else {
         d3 outward;
-        if (h.x == REC_SPHERE) {
+        if (h.x <= REC_MSPHERE) {
             d3 c = mk(ldg_d(d), ldg_d(d + 1), ldg_d(d + 2));
             double r = ldg_d(d + 3);
-            outward = mk((p.x - c.x) / r, (p.y - c.y) / r, (p.z - c.z) / r);  // hittable.rs:111
-            if (kPrecise) sphere_uv(outward, out.u, out.v);
-        } else if (h.x == REC_MSPHERE) {
-            double dd[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) dd[k] = ldg_d(d + k);
-            d3 c = msphere_center(dd, ray.time);
-            outward = mk((p.x - c.x) / dd[6], (p.y - c.y) / dd[6], (p.z - c.z) / dd[6]);  // hittable.rs:219; u = v = 0 (Q10)
+            if (h.x == REC_MSPHERE) {  // MovingSphere::center, hittable.rs:187-191; u = v = 0 (Q10)
+                double f = (ray.time - ldg_d(d + 7)) * ldg_d(d + 8);
+                c = mk(c.x + f * r, c.y + f * ldg_d(d + 4), c.z + f * ldg_d(d + 5));
+                r = ldg_d(d + 6);
+            }
+            outward = mk((p.x - c.x) / r, (p.y - c.y) / r, (p.z - c.z) / r);  // hittable.rs:111,219
+            if (kPrecise && h.x == REC_SPHERE) sphere_uv(outward, out.u, out.v);
         } else {
             int plane = h.x - REC_RECT_XY;
             int a0 = plane == 2 ? 1 : 0, a1 = plane == 0 ? 1 : 2;
@@ -580,9 +591,13 @@ __device__ __forceinline__ float perlin_turbulence(const DPerlin* tab, float px,
 __device__ __forceinline__ f3 texture_value(const SceneView& sc, int32_t ti, float u, float v, d3 p) {
     DTexture t = sc.textures[ti];
     // CheckerTexture (texture.rs:15-30, Q21) selects a child; children may nest
+#pragma unroll 1
     for (int guard = 0; guard < 8 && t.kind == RTX_TEX_CHECKER; ++guard) {
-        // f64 products keep the stripe edges of the radius-1000 ground sphere where the reference puts them
-        float sines = sinf((float)(10.0 * p.x)) * sinf((float)(10.0 * p.y)) * sinf((float)(10.0 * p.z));
+        // f64 products keep the stripe edges of the radius-1000 ground sphere where the reference puts them;
+        // one sinf call site (its large-argument reduction is ~500 instructions of code)
+        float sines = 1.f;
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) sines *= sinf((float)(10.0 * comp(p, c)));
         t = sc.textures[sines < 0.f ? t.a : t.b];
     }
     if (t.kind == RTX_TEX_SOLID) return mkf(t.f[0], t.f[1], t.f[2]);
@@ -625,6 +640,7 @@ struct RenderArgs {
     int32_t tiles_x, tiles_y;
     // phase scheduling weights (see render_kernel): a phase runs when weight * lanes waiting for it is the largest
     int32_t w_node, w_leaf, w_shade;
+    int32_t node_burst;  // node steps per vote, at most
 };
 
 constexpr int kTileW = 8, kTileH = 4;  // work tile = 8x4 pixels x spp_count samples
@@ -703,12 +719,26 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
 
         if (s_node >= s_leaf && s_node >= s_shade) {
             // ================= node phase =================
-            if (want_node) cur = node_step(a.sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
+            // a burst of node steps: stay while at least half of the lanes that started it still have a node
+            bool go = want_node;
+#pragma unroll 1
+            for (int it = 0; it < a.node_burst; ++it) {
+                if (go) {
+                    cur = node_step(a.sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
+                    if (cur < 0 && cur != kSentinel && cur != kLeaveInstance && pending == 0) {
+                        pending = cur;  // postpone the leaf, keep traversing
+                        cur = stack[--sp];
+                    }
+                    go = cur >= 0;
+                }
+                if (2 * __popc(__ballot_sync(FULL, go)) < n_node) break;
+            }
         } else if (s_leaf >= s_shade) {
             // ================= leaf phase =================
             if (want_leaf) {
+                d3 o = ray.o, d = ray.d;
+                bool reslab = false;
                 if (pending != 0) {
-                    d3 o = ray.o, d = ray.d;
                     if (cur_chain != 0) to_space(a.sc, cur_chain, o, d);
                     int32_t v = ~pending;
                     int32_t first = v >> 4, count = v & 15;
@@ -718,10 +748,10 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                         int4 h = __ldg(reinterpret_cast<const int4*>(rp));
                         if (h.x == REC_INSTANCE) {  // Translate / YRotate::hit: re-express the ray, descend
                             tally.instance();
-                            cur_chain = h.w | (h.z << 24);
+                            cur_chain = h.w;
                             o = ray.o; d = ray.d;
                             to_space(a.sc, cur_chain, o, d);
-                            make_slab(o, d, sr);
+                            reslab = true;
                             stack[sp++] = cur;
                             stack[sp++] = kLeaveInstance;
                             cur = h.y;
@@ -737,10 +767,12 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                     }
                 }
                 if (cur == kLeaveInstance) {  // back to world space
-                    make_slab(ray.o, ray.d, sr);
+                    o = ray.o; d = ray.d;
+                    reslab = true;
                     cur_chain = 0;
                     cur = stack[--sp];
                 }
+                if (reslab) make_slab(o, d, sr);
             }
         } else {
             // ================= shade phase =================
@@ -763,66 +795,76 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                         DMaterial m = a.sc.materials[ho.material];
                         mkind = m.kind; mtex = m.texture; alb_r = m.albedo[0]; alb_g = m.albedo[1]; alb_b = m.albedo[2]; mparam = m.param;
                     }
-                    float tu = (float)ho.u, tv = (float)ho.v;
-                    if (mtex >= 0 && ho.type == REC_SPHERE && a.sc.textures[mtex]._pad) {
-                        // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
-                        const float PI = 3.14159265358979f;
-                        tv = acosf(-(float)ho.on.y) / PI;
-                        tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+                    // Texture::value for the three materials that carry one (material.rs:97,247,262)
+                    if (mkind == RTX_MAT_LAMBERTIAN || mkind == RTX_MAT_ISOTROPIC || mkind == RTX_MAT_DIFFUSE_LIGHT) {
+                        float tu = (float)ho.u, tv = (float)ho.v;
+                        if (ho.type == REC_SPHERE && a.sc.textures[mtex]._pad) {
+                            // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
+                            const float PI = 3.14159265358979f;
+                            tv = acosf(-(float)ho.on.y) / PI;
+                            tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+                        }
+                        f3 tex = texture_value(a.sc, mtex, tu, tv, ho.p);
+                        alb_r = tex.x; alb_g = tex.y; alb_b = tex.z;
                     }
-                    d3 udir;
                     if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
-                        f3 e = texture_value(a.sc, mtex, tu, tv, ho.p);
-                        rad_r += thr_r * e.x; rad_g += thr_g * e.y; rad_b += thr_b * e.z;
+                        rad_r += thr_r * alb_r; rad_g += thr_g * alb_g; rad_b += thr_b * alb_b;
                         end_path = true;
-                    } else if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
-                        d3 b = random_in_unit_space(smp);
-                        ray.d = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
-                        f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
-                        thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
-                    } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
-                        ray.d = random_in_unit_space(smp);
-                        f3 att = texture_value(a.sc, mtex, tu, tv, ho.p);
-                        thr_r *= att.x; thr_g *= att.y; thr_b *= att.z;
-                    } else if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
-                        double k = 1.0 / sqrt(dot(ray.d, ray.d));
-                        udir = k * ray.d;
-                        d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
-                        d3 b = random_in_unit_space(smp);
-                        d3 nd = refl + (double)mparam * b;
-                        if (dot(nd, ho.n) > 0.0) {
-                            ray.d = nd;
-                            thr_r *= alb_r; thr_g *= alb_g; thr_b *= alb_b;
+                    } else {
+                        // The random draws of scatter(): block (SCATTER, 0) serves every material — words 0..2 are the
+                        // first candidate of Vec3f::random_in_unit_space (vec3.rs:149-160; Lambertian, Isotropic and
+                        // Metal keep drawing blocks until one lies in the ball), word 3 the Dielectric's uniform
+                        // (material.rs:189). The candidates are exact in fp32 and their squared length is exact in f64,
+                        // so accept / reject decisions are the oracle's.
+                        const bool ball = mkind != RTX_MAT_DIELECTRIC;
+                        d3 b;
+                        uint32_t w3 = 0;
+                        for (uint32_t j = 0;; ++j) {
+                            uint4 w = smp.block(P_SCATTER, j);
+                            if (j == 0) w3 = w.w;
+                            b = mk(2.0 * u01d(w.x) - 1.0, 2.0 * u01d(w.y) - 1.0, 2.0 * u01d(w.z) - 1.0);
+                            if (!ball || dot(b, b) < 1.0) break;
+                        }
+                        d3 nd;
+                        if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
+                            nd = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
+                        } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
+                            nd = b;
                         } else {
-                            end_path = true;  // absorbed: only `emitted` (= 0) is returned
+                            double k = 1.0 / sqrt(dot(ray.d, ray.d));
+                            d3 udir = k * ray.d;  // Vec3f::unit of the incoming direction
+                            d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
+                            if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
+                                nd = refl + (double)mparam * b;
+                                if (!(dot(nd, ho.n) > 0.0)) end_path = true;  // absorbed: only `emitted` (= 0) is returned
+                            } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
+                                double ir = (double)mparam;
+                                double ratio = ho.front_face ? 1.0 / ir : ir;
+                                double cos_theta = fmin(dot(-udir, ho.n), 1.0);
+                                double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+                                bool reflect = ratio * sin_theta > 1.0;
+                                if (!reflect) {
+                                    double r0 = (1.0 - ratio) / (1.0 + ratio);
+                                    r0 = r0 * r0;
+                                    double om = 1.0 - cos_theta;
+                                    double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
+                                    reflect = schlick > u01d(w3);
+                                }
+                                nd = refl;
+                                if (!reflect) {  // vec3.rs:116-121
+                                    d3 perp = ratio * (udir + cos_theta * ho.n);
+                                    d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
+                                    nd = perp + par;
+                                }
+                                alb_r = alb_g = alb_b = 1.f;
+                            }
                         }
-                    } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
-                        double ir = (double)mparam;
-                        double ratio = ho.front_face ? 1.0 / ir : ir;
-                        double k = 1.0 / sqrt(dot(ray.d, ray.d));
-                        udir = k * ray.d;
-                        double cos_theta = fmin(dot(-udir, ho.n), 1.0);
-                        double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
-                        bool reflect = ratio * sin_theta > 1.0;
-                        if (!reflect) {
-                            double r0 = (1.0 - ratio) / (1.0 + ratio);
-                            r0 = r0 * r0;
-                            double om = 1.0 - cos_theta;
-                            double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
-                            uint4 w = smp.block(P_SCATTER, 0);
-                            reflect = schlick > u01d(w.w);
-                        }
-                        if (reflect) {
-                            ray.d = udir - (2.0 * dot(udir, ho.n)) * ho.n;
-                        } else {  // vec3.rs:116-121
-                            d3 perp = ratio * (udir + cos_theta * ho.n);
-                            d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
-                            ray.d = perp + par;
-                        }
+                        thr_r *= alb_r; thr_g *= alb_g; thr_b *= alb_b;
+                        ray.d = nd;
+                        ray.o = ho.p;
+                        ++bounce;
+                        if (bounce >= a.max_depth) end_path = true;  // color(depth = 0) returns 0
                     }
-                    ray.o = ho.p;
-                    ++bounce;
-                    if (bounce >= a.max_depth) end_path = true;  // color(depth = 0) returns 0
                 }
                 if (end_path) {
                     // one path sample done: add it to its pixel (sum r, g, b, count)
@@ -870,17 +912,21 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                         if (a.max_depth <= 0) {  // color(.., depth = 0) is black without tracing anything (main.rs:27-29)
                             atomicAdd(accum + smp.pixel, make_float4(0.f, 0.f, 0.f, 1.0f));
                         } else {
-                            // pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25)
-                            uint4 w = smp.block(P_CAMERA, 0);
-                            double su = ((double)px + u01d(w.x)) / (double)a.width;
-                            double sv = ((double)jrow + u01d(w.y)) / (double)a.height;
-                            double lx = 0.0, ly = 0.0;
-                            if (a.cam.lens_radius != 0.0) {  // the draw is skipped for a pinhole: counters make that invisible
-                                for (uint32_t j = 0;; ++j) {
-                                    uint4 l = smp.block(P_LENS, j);
-                                    lx = 2.0 * u01d(l.x) - 1.0; ly = 2.0 * u01d(l.y) - 1.0;
+                            // pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25): block (CAMERA, 0)
+                            // holds the jitter and the shutter time, blocks (LENS, j) two disk candidates each. The
+                            // lens draw is skipped for a pinhole: counter-based draws make that invisible.
+                            double su = 0.0, sv = 0.0, tm = 0.0, lx = 0.0, ly = 0.0;
+                            for (uint32_t j = 0;; ++j) {
+                                uint4 w = smp.block(j == 0 ? P_CAMERA : P_LENS, j == 0 ? 0u : j - 1u);
+                                if (j == 0) {
+                                    su = ((double)px + u01d(w.x)) / (double)a.width;
+                                    sv = ((double)jrow + u01d(w.y)) / (double)a.height;
+                                    tm = u01d(w.z);
+                                    if (a.cam.lens_radius == 0.0) break;
+                                } else {
+                                    lx = 2.0 * u01d(w.x) - 1.0; ly = 2.0 * u01d(w.y) - 1.0;
                                     if (lx * lx + ly * ly < 1.0) break;
-                                    lx = 2.0 * u01d(l.z) - 1.0; ly = 2.0 * u01d(l.w) - 1.0;
+                                    lx = 2.0 * u01d(w.z) - 1.0; ly = 2.0 * u01d(w.w) - 1.0;
                                     if (lx * lx + ly * ly < 1.0) break;
                                 }
                             }
@@ -890,7 +936,7 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                             ray.d = mk(a.cam.lower_left[0] + su * a.cam.horizontal[0] + sv * a.cam.vertical[0] - a.cam.origin[0] - off.x,
                                        a.cam.lower_left[1] + su * a.cam.horizontal[1] + sv * a.cam.vertical[1] - a.cam.origin[1] - off.y,
                                        a.cam.lower_left[2] + su * a.cam.horizontal[2] + sv * a.cam.vertical[2] - a.cam.origin[2] - off.z);
-                            ray.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01d(w.z);
+                            ray.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * tm;
                             thr_r = thr_g = thr_b = 1.f;
                             rad_r = rad_g = rad_b = 0.f;
                             bounce = 0;

@@ -215,7 +215,7 @@ def test_ten_million_rays_final_scene(ctx, earth_rgba):
     h1 = d_hits.cpu().numpy().view(abi.HIT_DTYPE)
     secondary = RY.secondary_rays(h1, primary, rng)
     m = secondary.shape[0]
-    assert m > 0.9 * half  # the fog sphere encloses the scene: nearly every ray hits something
+    assert m > 0.6 * half  # ground, objects, and ~39% of the sky rays scatter in the r = 5000 fog
     d_rays2 = torch.from_numpy(secondary.view(np.uint8).reshape(-1)).cuda()
     d_hits2 = torch.empty(m * 88, dtype=torch.uint8, device="cuda")
     gsc.trace_device(d_rays2, d_hits2, m)
