@@ -42,6 +42,15 @@ struct rtx_ctx {
     unsigned int* d_work_counter = nullptr;  // render_kernel's tile dispenser
     rtx::Counters* d_counters = nullptr;
     int node_burst = 4;
+    int mode = 1;  // 1: wavefront (default), 0: megakernel (RTX_MODE=mega)
+    // wavefront state, allocated at the first render
+    void* d_pool = nullptr;
+    int pool_slots = 0, pool_slots_wanted = 1 << 20;
+    unsigned long long* d_next_item = nullptr;
+    unsigned int* d_active = nullptr;            // [2]
+    unsigned long long* h_status = nullptr;      // pinned: [2][2] = {active, next_item} per batch parity
+    cudaEvent_t batch_done[2] = {nullptr, nullptr};
+    int wf_batch = 8;
     int w_node = 1, w_leaf = 1, w_shade = 1;  // render_kernel phase weights (RTX_W_NODE / RTX_W_LEAF / RTX_W_SHADE override)
 };
 
@@ -101,6 +110,9 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->w_leaf = env_int("RTX_W_LEAF", c->w_leaf);
     c->w_shade = env_int("RTX_W_SHADE", c->w_shade);
     c->node_burst = env_int("RTX_NODE_BURST", c->node_burst);
+    c->pool_slots_wanted = env_int("RTX_WF_SLOTS", c->pool_slots_wanted);
+    c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
+    if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -114,6 +126,12 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_work_counter);
     cudaFree(c->d_counters);
+    cudaFree(c->d_pool);
+    cudaFree(c->d_next_item);
+    cudaFree(c->d_active);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    for (auto& e : c->batch_done)
+        if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTX_OK;
@@ -302,6 +320,97 @@ int rtx_trace_rays_stats(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ra
     return RTX_OK;
 }
 
+// ---- render: wavefront driver ---------------------------------------------------
+static int wf_prepare(rtx_ctx* c, int64_t slots) {
+    if (slots > c->pool_slots) {
+        if (c->d_pool) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->d_pool)); c->d_pool = nullptr; c->pool_slots = 0; }
+        CU(cudaMalloc(&c->d_pool, (size_t)slots * rtx::kPoolBytesPerSlot + 256));
+        c->pool_slots = (int)slots;
+    }
+    if (!c->d_next_item) CU(cudaMalloc(&c->d_next_item, sizeof(unsigned long long)));
+    if (!c->d_active) CU(cudaMalloc(&c->d_active, 2 * sizeof(unsigned int)));
+    if (!c->h_status) CU(cudaMallocHost(&c->h_status, 4 * sizeof(unsigned long long)));
+    for (auto& e : c->batch_done)
+        if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return RTX_OK;
+}
+
+// Submits iterations (shade, trace) in batches; after each batch the number of rays the batch's
+// last shade kernel produced and the dispenser position are copied to pinned memory. The host looks
+// at batch k-1 while batch k is already queued, so the GPU never waits for the host; it stops
+// submitting once a batch ended with no ray in flight and no sample left (the batch queued behind it
+// then runs over empty slots). The call returns when everything has been submitted AND that check
+// has come back, i.e. it may block the calling thread for most of the render.
+static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum,
+                            unsigned long long* d_ray_count, bool counted) {
+    const int64_t n_tiles = (int64_t)((p->width + rtx::kTileW - 1) / rtx::kTileW) * ((p->height + rtx::kTileH - 1) / rtx::kTileH);
+    const unsigned long long total = (unsigned long long)n_tiles * 32ull * (unsigned long long)p->spp_count;
+    int64_t slots = c->pool_slots_wanted;
+    if ((unsigned long long)slots > total) slots = (int64_t)((total + 127) / 128 * 128);
+    int rc = wf_prepare(c, slots);
+    if (rc != RTX_OK) return rc;
+    rtx::WfArgs a;
+    a.sc = s->view;
+    a.cam = s->camera;
+    a.width = p->width; a.height = p->height;
+    a.spp_begin = p->spp_begin; a.spp_count = p->spp_count; a.max_depth = p->max_depth;
+    a.k0 = (uint32_t)p->seed; a.k1 = (uint32_t)(p->seed >> 32);
+    a.tiles_x = (p->width + rtx::kTileW - 1) / rtx::kTileW;
+    a.tiles_y = (p->height + rtx::kTileH - 1) / rtx::kTileH;
+    a.n_slots = (int32_t)slots;
+    a.total_items = total;
+    a.next_item = c->d_next_item;
+    {   // carve the SoA arrays out of the pool allocation (8-byte arrays first)
+        uint8_t* base = (uint8_t*)c->d_pool;
+        size_t n = (size_t)slots;
+        double** d8[8] = {&a.pool.ox, &a.pool.oy, &a.pool.oz, &a.pool.dx, &a.pool.dy, &a.pool.dz, &a.pool.time, &a.pool.best_t};
+        for (auto pp : d8) { *pp = (double*)base; base += n * 8; }
+        a.pool.best_rec = (int32_t*)base; base += n * 4;
+        a.pool.best_chain = (int32_t*)base; base += n * 4;
+        a.pool.bounce = (int32_t*)base; base += n * 4;
+        a.pool.pixel = (uint32_t*)base; base += n * 4;
+        a.pool.sample = (uint32_t*)base; base += n * 4;
+        float** f4[6] = {&a.pool.thr_r, &a.pool.thr_g, &a.pool.thr_b, &a.pool.rad_r, &a.pool.rad_g, &a.pool.rad_b};
+        for (auto pp : f4) { *pp = (float*)base; base += n * 4; }
+    }
+    CU(cudaMemsetAsync(a.pool.bounce, 0xFF, (size_t)slots * 4, c->stream));  // every slot empty (-1)
+    CU(cudaMemsetAsync(c->d_next_item, 0, sizeof(unsigned long long), c->stream));
+    float4* acc = reinterpret_cast<float4*>(d_accum);
+    const unsigned grid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
+    const int batch = c->wf_batch;
+    for (int k = 0;; ++k) {
+        const int par = k & 1;
+        for (int it = 0; it < batch; ++it) {
+            unsigned int* active = nullptr;
+            if (it == batch - 1) {
+                active = c->d_active + par;
+                CU(cudaMemsetAsync(active, 0, sizeof(unsigned int), c->stream));
+            }
+            if (counted) {
+                rtx::wf_shade_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
+                rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
+            } else {
+                rtx::wf_shade_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, nullptr);
+                rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);
+            }
+        }
+        CU(cudaGetLastError());
+        // status of this batch -> pinned memory (active is 32-bit: widen on the host side)
+        c->h_status[2 * par] = 0;
+        CU(cudaMemcpyAsync(&c->h_status[2 * par], c->d_active + par, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&c->h_status[2 * par + 1], c->d_next_item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->batch_done[par], c->stream));
+        if (k >= 1) {  // look at the previous batch while this one runs
+            const int prev = par ^ 1;
+            CU(cudaEventSynchronize(c->batch_done[prev]));
+            if ((unsigned int)c->h_status[2 * prev] == 0 && c->h_status[2 * prev + 1] >= total) break;
+        }
+    }
+    // the batch queued behind the one that ended dry runs over empty slots only; later calls on this
+    // stream are ordered after it
+    return RTX_OK;
+}
+
 // ---- render -----------------------------------------------------------------
 static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum,
                          unsigned long long* d_ray_count, bool counted) {
@@ -312,6 +421,13 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     if (p->spp_count > (1 << 26)) return fail(RTX_ERR_INVALID, "more than 2^26 samples per pixel in one call");
     if (p->spp_count == 0) return RTX_OK;
     CU(cudaSetDevice(c->device));
+    if (p->max_depth == 0) {  // color(.., depth = 0) is black (main.rs:27-29): only the sample counts move
+        int n = p->width * p->height;
+        rtx::add_black_samples_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<float4*>(d_accum), n, (float)p->spp_count);
+        CU(cudaGetLastError());
+        return RTX_OK;
+    }
+    if (c->mode == 1) return render_wavefront(c, s, p, d_accum, d_ray_count, counted);
     rtx::RenderArgs a;
     a.sc = s->view;
     a.cam = s->camera;

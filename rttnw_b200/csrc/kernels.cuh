@@ -632,6 +632,138 @@ __device__ __forceinline__ d3 random_in_unit_space(const Sampler& smp) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// One level of color() (main.rs:26-45, Q7) for a ray whose closest hit is known: adds the emitted /
+// background radiance, scatters (Material::scatter) and leaves the next ray in `ray`. Returns true
+// when the path ends here. Shared by the megakernel's shade phase and the wavefront shade kernel.
+// ---------------------------------------------------------------------------
+struct PathColor {
+    float thr_r, thr_g, thr_b;  // product of the attenuations so far
+    float rad_r, rad_g, rad_b;  // radiance gathered so far
+};
+
+__device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __restrict__ background, int32_t max_depth, RayD& ray,
+                                          const Best& best, const Sampler& smp, PathColor& pc, int& bounce) {
+    bool end_path = false;
+    if (best.rec < 0) {  // background (Q8)
+        pc.rad_r += pc.thr_r * background[0]; pc.rad_g += pc.thr_g * background[1]; pc.rad_b += pc.thr_b * background[2];
+        end_path = true;
+    } else {
+        HitOut ho;
+        finalize_hit<false>(sc, ray, best, ho);
+        int32_t mkind, mtex;
+        float alb_r = 0.f, alb_g = 0.f, alb_b = 0.f, mparam = 0.f;
+        if (ho.material < 0) {  // ConstantMedium's own Isotropic (hittable.rs:726,786)
+            mkind = RTX_MAT_ISOTROPIC;
+            mtex = -(ho.material + 1);
+        } else {
+            DMaterial m = sc.materials[ho.material];
+            mkind = m.kind; mtex = m.texture; alb_r = m.albedo[0]; alb_g = m.albedo[1]; alb_b = m.albedo[2]; mparam = m.param;
+        }
+        // Texture::value for the three materials that carry one (material.rs:97,247,262)
+        if (mkind == RTX_MAT_LAMBERTIAN || mkind == RTX_MAT_ISOTROPIC || mkind == RTX_MAT_DIFFUSE_LIGHT) {
+            float tu = (float)ho.u, tv = (float)ho.v;
+            if (ho.type == REC_SPHERE && sc.textures[mtex]._pad) {
+                // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
+                const float PI = 3.14159265358979f;
+                tv = acosf(-(float)ho.on.y) / PI;
+                tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+            }
+            f3 tex = texture_value(sc, mtex, tu, tv, ho.p);
+            alb_r = tex.x; alb_g = tex.y; alb_b = tex.z;
+        }
+        if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
+            pc.rad_r += pc.thr_r * alb_r; pc.rad_g += pc.thr_g * alb_g; pc.rad_b += pc.thr_b * alb_b;
+            end_path = true;
+        } else {
+            // The random draws of scatter(): block (SCATTER, 0) serves every material — words 0..2 are the
+            // first candidate of Vec3f::random_in_unit_space (vec3.rs:149-160; Lambertian, Isotropic and
+            // Metal keep drawing blocks until one lies in the ball), word 3 the Dielectric's uniform
+            // (material.rs:189). The candidates are exact in fp32 and their squared length is exact in f64,
+            // so accept / reject decisions are the oracle's.
+            const bool ball = mkind != RTX_MAT_DIELECTRIC;
+            d3 b;
+            uint32_t w3 = 0;
+            for (uint32_t j = 0;; ++j) {
+                uint4 w = smp.block(P_SCATTER, j);
+                if (j == 0) w3 = w.w;
+                b = mk(2.0 * u01d(w.x) - 1.0, 2.0 * u01d(w.y) - 1.0, 2.0 * u01d(w.z) - 1.0);
+                if (!ball || dot(b, b) < 1.0) break;
+            }
+            d3 nd;
+            if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
+                nd = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
+            } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
+                nd = b;
+            } else {
+                double k = 1.0 / sqrt(dot(ray.d, ray.d));
+                d3 udir = k * ray.d;  // Vec3f::unit of the incoming direction
+                d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
+                if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
+                    nd = refl + (double)mparam * b;
+                    if (!(dot(nd, ho.n) > 0.0)) end_path = true;  // absorbed: only `emitted` (= 0) is returned
+                } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
+                    double ir = (double)mparam;
+                    double ratio = ho.front_face ? 1.0 / ir : ir;
+                    double cos_theta = fmin(dot(-udir, ho.n), 1.0);
+                    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+                    bool reflect = ratio * sin_theta > 1.0;
+                    if (!reflect) {
+                        double r0 = (1.0 - ratio) / (1.0 + ratio);
+                        r0 = r0 * r0;
+                        double om = 1.0 - cos_theta;
+                        double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
+                        reflect = schlick > u01d(w3);
+                    }
+                    nd = refl;
+                    if (!reflect) {  // vec3.rs:116-121
+                        d3 perp = ratio * (udir + cos_theta * ho.n);
+                        d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
+                        nd = perp + par;
+                    }
+                    alb_r = alb_g = alb_b = 1.f;
+                }
+            }
+            pc.thr_r *= alb_r; pc.thr_g *= alb_g; pc.thr_b *= alb_b;
+            ray.d = nd;
+            ray.o = ho.p;
+            ++bounce;
+            if (bounce >= max_depth) end_path = true;  // color(depth = 0) returns 0
+        }
+    }
+    return end_path;
+}
+
+// Pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25) for pixel column `px`, row `jrow`
+// counted from the bottom (main.rs:202-204), sample smp.sample.
+__device__ __forceinline__ void camera_ray(const CameraView& cam, int width, int height, int px, int jrow, const Sampler& smp, RayD& ray) {
+    // pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25): block (CAMERA, 0)
+    // holds the jitter and the shutter time, blocks (LENS, j) two disk candidates each. The
+    // lens draw is skipped for a pinhole: counter-based draws make that invisible.
+    double su = 0.0, sv = 0.0, tm = 0.0, lx = 0.0, ly = 0.0;
+    for (uint32_t j = 0;; ++j) {
+        uint4 w = smp.block(j == 0 ? P_CAMERA : P_LENS, j == 0 ? 0u : j - 1u);
+        if (j == 0) {
+            su = ((double)px + u01d(w.x)) / (double)width;
+            sv = ((double)jrow + u01d(w.y)) / (double)height;
+            tm = u01d(w.z);
+            if (cam.lens_radius == 0.0) break;
+        } else {
+            lx = 2.0 * u01d(w.x) - 1.0; ly = 2.0 * u01d(w.y) - 1.0;
+            if (lx * lx + ly * ly < 1.0) break;
+            lx = 2.0 * u01d(w.z) - 1.0; ly = 2.0 * u01d(w.w) - 1.0;
+            if (lx * lx + ly * ly < 1.0) break;
+        }
+    }
+    double rdx = cam.lens_radius * lx, rdy = cam.lens_radius * ly;
+    d3 off = mk(cam.u[0] * rdx + cam.v[0] * rdy, cam.u[1] * rdx + cam.v[1] * rdy, cam.u[2] * rdx + cam.v[2] * rdy);
+    ray.o = mk(cam.origin[0] + off.x, cam.origin[1] + off.y, cam.origin[2] + off.z);
+    ray.d = mk(cam.lower_left[0] + su * cam.horizontal[0] + sv * cam.vertical[0] - cam.origin[0] - off.x,
+               cam.lower_left[1] + su * cam.horizontal[1] + sv * cam.vertical[1] - cam.origin[1] - off.y,
+               cam.lower_left[2] + su * cam.horizontal[2] + sv * cam.vertical[2] - cam.origin[2] - off.z);
+    ray.time = cam.time0 + (cam.time1 - cam.time0) * tm;
+}
+
 struct RenderArgs {
     SceneView sc;
     CameraView cam;
@@ -690,7 +822,7 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
     int32_t cur = kSentinel, pending = 0, cur_chain = 0;  // pending: a postponed leaf (leaf codes are negative; 0 = none)
     int sp = 0;
     Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
-    float thr_r = 1.f, thr_g = 1.f, thr_b = 1.f, rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
+    PathColor pc{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
     int bounce = 0;
     unsigned long long my_rays = 0;
 
@@ -778,97 +910,10 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
             // ================= shade phase =================
             bool fresh = false;  // this lane leaves the phase with a new ray to trace
             if (st == ST_SHADE) {
-                // ---- color(), main.rs:26-45, one level (Q7) ----
-                bool end_path = false;
-                if (best.rec < 0) {  // background (Q8)
-                    rad_r += thr_r * a.cam.background[0]; rad_g += thr_g * a.cam.background[1]; rad_b += thr_b * a.cam.background[2];
-                    end_path = true;
-                } else {
-                    HitOut ho;
-                    finalize_hit<false>(a.sc, ray, best, ho);
-                    int32_t mkind, mtex;
-                    float alb_r = 0.f, alb_g = 0.f, alb_b = 0.f, mparam = 0.f;
-                    if (ho.material < 0) {  // ConstantMedium's own Isotropic (hittable.rs:726,786)
-                        mkind = RTX_MAT_ISOTROPIC;
-                        mtex = -(ho.material + 1);
-                    } else {
-                        DMaterial m = a.sc.materials[ho.material];
-                        mkind = m.kind; mtex = m.texture; alb_r = m.albedo[0]; alb_g = m.albedo[1]; alb_b = m.albedo[2]; mparam = m.param;
-                    }
-                    // Texture::value for the three materials that carry one (material.rs:97,247,262)
-                    if (mkind == RTX_MAT_LAMBERTIAN || mkind == RTX_MAT_ISOTROPIC || mkind == RTX_MAT_DIFFUSE_LIGHT) {
-                        float tu = (float)ho.u, tv = (float)ho.v;
-                        if (ho.type == REC_SPHERE && a.sc.textures[mtex]._pad) {
-                            // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
-                            const float PI = 3.14159265358979f;
-                            tv = acosf(-(float)ho.on.y) / PI;
-                            tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
-                        }
-                        f3 tex = texture_value(a.sc, mtex, tu, tv, ho.p);
-                        alb_r = tex.x; alb_g = tex.y; alb_b = tex.z;
-                    }
-                    if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
-                        rad_r += thr_r * alb_r; rad_g += thr_g * alb_g; rad_b += thr_b * alb_b;
-                        end_path = true;
-                    } else {
-                        // The random draws of scatter(): block (SCATTER, 0) serves every material — words 0..2 are the
-                        // first candidate of Vec3f::random_in_unit_space (vec3.rs:149-160; Lambertian, Isotropic and
-                        // Metal keep drawing blocks until one lies in the ball), word 3 the Dielectric's uniform
-                        // (material.rs:189). The candidates are exact in fp32 and their squared length is exact in f64,
-                        // so accept / reject decisions are the oracle's.
-                        const bool ball = mkind != RTX_MAT_DIELECTRIC;
-                        d3 b;
-                        uint32_t w3 = 0;
-                        for (uint32_t j = 0;; ++j) {
-                            uint4 w = smp.block(P_SCATTER, j);
-                            if (j == 0) w3 = w.w;
-                            b = mk(2.0 * u01d(w.x) - 1.0, 2.0 * u01d(w.y) - 1.0, 2.0 * u01d(w.z) - 1.0);
-                            if (!ball || dot(b, b) < 1.0) break;
-                        }
-                        d3 nd;
-                        if (mkind == RTX_MAT_LAMBERTIAN) {  // material.rs:90-99 (Q2)
-                            nd = mk(ho.p.x + ho.n.x + b.x - ho.p.x, ho.p.y + ho.n.y + b.y - ho.p.y, ho.p.z + ho.n.z + b.z - ho.p.z);
-                        } else if (mkind == RTX_MAT_ISOTROPIC) {  // material.rs:256-266 (Q3)
-                            nd = b;
-                        } else {
-                            double k = 1.0 / sqrt(dot(ray.d, ray.d));
-                            d3 udir = k * ray.d;  // Vec3f::unit of the incoming direction
-                            d3 refl = udir - (2.0 * dot(udir, ho.n)) * ho.n;
-                            if (mkind == RTX_MAT_METAL) {  // material.rs:134-148 (Q4)
-                                nd = refl + (double)mparam * b;
-                                if (!(dot(nd, ho.n) > 0.0)) end_path = true;  // absorbed: only `emitted` (= 0) is returned
-                            } else {  // RTX_MAT_DIELECTRIC, material.rs:180-203 (Q5, Q6); attenuation (1,1,1)
-                                double ir = (double)mparam;
-                                double ratio = ho.front_face ? 1.0 / ir : ir;
-                                double cos_theta = fmin(dot(-udir, ho.n), 1.0);
-                                double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
-                                bool reflect = ratio * sin_theta > 1.0;
-                                if (!reflect) {
-                                    double r0 = (1.0 - ratio) / (1.0 + ratio);
-                                    r0 = r0 * r0;
-                                    double om = 1.0 - cos_theta;
-                                    double schlick = r0 + (1.0 - r0) * (om * om * om * om * om);
-                                    reflect = schlick > u01d(w3);
-                                }
-                                nd = refl;
-                                if (!reflect) {  // vec3.rs:116-121
-                                    d3 perp = ratio * (udir + cos_theta * ho.n);
-                                    d3 par = (-sqrt(fabs(1.0 - dot(perp, perp)))) * ho.n;
-                                    nd = perp + par;
-                                }
-                                alb_r = alb_g = alb_b = 1.f;
-                            }
-                        }
-                        thr_r *= alb_r; thr_g *= alb_g; thr_b *= alb_b;
-                        ray.d = nd;
-                        ray.o = ho.p;
-                        ++bounce;
-                        if (bounce >= a.max_depth) end_path = true;  // color(depth = 0) returns 0
-                    }
-                }
+                const bool end_path = shade_hit(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce);
                 if (end_path) {
                     // one path sample done: add it to its pixel (sum r, g, b, count)
-                    atomicAdd(accum + smp.pixel, make_float4(rad_r, rad_g, rad_b, 1.0f));
+                    atomicAdd(accum + smp.pixel, make_float4(pc.rad_r, pc.rad_g, pc.rad_b, 1.0f));
                     st = ST_NEW;
                 } else {
                     fresh = true;
@@ -912,33 +957,8 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                         if (a.max_depth <= 0) {  // color(.., depth = 0) is black without tracing anything (main.rs:27-29)
                             atomicAdd(accum + smp.pixel, make_float4(0.f, 0.f, 0.f, 1.0f));
                         } else {
-                            // pixel jitter (main.rs:212-214) + Camera::ray (camera.rs:63-84, Q25): block (CAMERA, 0)
-                            // holds the jitter and the shutter time, blocks (LENS, j) two disk candidates each. The
-                            // lens draw is skipped for a pinhole: counter-based draws make that invisible.
-                            double su = 0.0, sv = 0.0, tm = 0.0, lx = 0.0, ly = 0.0;
-                            for (uint32_t j = 0;; ++j) {
-                                uint4 w = smp.block(j == 0 ? P_CAMERA : P_LENS, j == 0 ? 0u : j - 1u);
-                                if (j == 0) {
-                                    su = ((double)px + u01d(w.x)) / (double)a.width;
-                                    sv = ((double)jrow + u01d(w.y)) / (double)a.height;
-                                    tm = u01d(w.z);
-                                    if (a.cam.lens_radius == 0.0) break;
-                                } else {
-                                    lx = 2.0 * u01d(w.x) - 1.0; ly = 2.0 * u01d(w.y) - 1.0;
-                                    if (lx * lx + ly * ly < 1.0) break;
-                                    lx = 2.0 * u01d(w.z) - 1.0; ly = 2.0 * u01d(w.w) - 1.0;
-                                    if (lx * lx + ly * ly < 1.0) break;
-                                }
-                            }
-                            double rdx = a.cam.lens_radius * lx, rdy = a.cam.lens_radius * ly;
-                            d3 off = mk(a.cam.u[0] * rdx + a.cam.v[0] * rdy, a.cam.u[1] * rdx + a.cam.v[1] * rdy, a.cam.u[2] * rdx + a.cam.v[2] * rdy);
-                            ray.o = mk(a.cam.origin[0] + off.x, a.cam.origin[1] + off.y, a.cam.origin[2] + off.z);
-                            ray.d = mk(a.cam.lower_left[0] + su * a.cam.horizontal[0] + sv * a.cam.vertical[0] - a.cam.origin[0] - off.x,
-                                       a.cam.lower_left[1] + su * a.cam.horizontal[1] + sv * a.cam.vertical[1] - a.cam.origin[1] - off.y,
-                                       a.cam.lower_left[2] + su * a.cam.horizontal[2] + sv * a.cam.vertical[2] - a.cam.origin[2] - off.z);
-                            ray.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * tm;
-                            thr_r = thr_g = thr_b = 1.f;
-                            rad_r = rad_g = rad_b = 0.f;
+                            camera_ray(a.cam, a.width, a.height, px, jrow, smp, ray);
+                            pc = PathColor{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
                             bounce = 0;
                             fresh = true;
                             st = ST_TRAV;
@@ -986,6 +1006,170 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
             atomicAdd(&counters->medium_tests, (unsigned long long)vals[4]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// K2w: the same path loop as a WAVEFRONT. Paths live in a pool of slots in HBM (SoA, 108 bytes per
+// slot, L2-resident at the default pool size); one iteration = wf_shade_kernel (every slot: shade
+// the hit found for its ray, scatter or end the path, refill empty slots with new camera rays, run
+// the medium pre-pass for the new ray) followed by wf_trace_kernel (every slot: closest surface
+// hit of its ray). Each kernel then has ONE kind of work per thread, which is what the
+// megakernel's warp votes try to recover; the price is the pool traffic (~300 B per ray).
+// ---------------------------------------------------------------------------
+struct PathPool {
+    double *ox, *oy, *oz, *dx, *dy, *dz, *time, *best_t;
+    int32_t *best_rec, *best_chain, *bounce;  // bounce < 0: empty slot
+    uint32_t *pixel, *sample;
+    float *thr_r, *thr_g, *thr_b, *rad_r, *rad_g, *rad_b;
+};
+constexpr int kPoolBytesPerSlot = 8 * 8 + 11 * 4;
+
+struct WfArgs {
+    SceneView sc;
+    CameraView cam;
+    PathPool pool;
+    int32_t width, height, spp_begin, spp_count, max_depth;
+    uint32_t k0, k1;
+    int32_t tiles_x, tiles_y;
+    int32_t n_slots;
+    unsigned long long total_items;   // tiles * 32 * spp_count
+    unsigned long long* next_item;    // global dispenser of path samples
+};
+
+constexpr int kWfBlock = 128;
+
+template <bool kCount>
+__global__ void __launch_bounds__(kWfBlock) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < a.n_slots;
+    int32_t stack[kStackSize];  // only a ConstantMedium with a general boundary traverses here
+    Tally<kCount> tally;
+    int bounce = valid ? a.pool.bounce[i] : -2;
+    RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
+    PathColor pc{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+    Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
+    bool fresh = false, dirty = false;
+    if (bounce >= 0) {
+        ray.o = mk(a.pool.ox[i], a.pool.oy[i], a.pool.oz[i]);
+        ray.d = mk(a.pool.dx[i], a.pool.dy[i], a.pool.dz[i]);
+        ray.time = a.pool.time[i];
+        Best best{a.pool.best_t[i], a.pool.best_rec[i], a.pool.best_chain[i]};
+        pc = PathColor{a.pool.thr_r[i], a.pool.thr_g[i], a.pool.thr_b[i], a.pool.rad_r[i], a.pool.rad_g[i], a.pool.rad_b[i]};
+        smp.pixel = a.pool.pixel[i];
+        smp.sample = a.pool.sample[i];
+        smp.bounce = (uint32_t)bounce;
+        if (shade_hit(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce)) {
+            atomicAdd(accum + smp.pixel, make_float4(pc.rad_r, pc.rad_g, pc.rad_b, 1.0f));  // one path sample done
+            bounce = -1;
+            dirty = true;
+        } else {
+            fresh = true;
+        }
+    }
+    // ---- refill empty slots: consecutive items are the 32 pixels of one tile at one sample index ----
+    const bool want = bounce == -1;
+    unsigned m = __ballot_sync(FULL, want);
+    if (m != 0 && __ldcg(a.next_item) >= a.total_items) m = 0;  // dispenser already dry: no atomic (warp-uniform up to a race that only costs one)
+    if (m != 0) {
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(a.next_item, (unsigned long long)__popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        const unsigned long long item = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+        if (want && item < a.total_items) {
+            const unsigned long long per_tile = 32ull * (unsigned long long)a.spp_count;
+            const unsigned int tile = (unsigned int)(item / per_tile);
+            const unsigned int in_tile = (unsigned int)(item - (unsigned long long)tile * per_tile);
+            const int pi = (int)(in_tile & 31u);
+            const int px = (int)(tile % (unsigned int)a.tiles_x) * kTileW + (pi & (kTileW - 1));
+            const int row = (int)(tile / (unsigned int)a.tiles_x) * kTileH + (pi / kTileW);  // row 0 = top
+            if (px < a.width && row < a.height) {  // (a pixel beyond a ragged image edge: the slot retries next iteration)
+                smp.pixel = (uint32_t)(row * a.width + px);
+                smp.sample = (uint32_t)a.spp_begin + (in_tile >> 5);
+                smp.bounce = 0;
+                camera_ray(a.cam, a.width, a.height, px, a.height - 1 - row, smp, ray);
+                pc = PathColor{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+                bounce = 0;
+                fresh = true;
+            }
+        }
+    }
+    if (fresh) {
+        // ---- the new ray: media first (their scatter point bounds the surface search), then out to the pool ----
+        smp.bounce = (uint32_t)bounce;
+        Best best{1.7976931348623157e308, -1, 0};
+        if (a.sc.n_media > 0) {
+            SlabRay sr;
+            make_slab(ray.o, ray.d, sr);
+            media_prepass<false>(a.sc, ray, sr, 0.001, best, 0.0, &smp, stack, tally);
+        }
+        a.pool.ox[i] = ray.o.x; a.pool.oy[i] = ray.o.y; a.pool.oz[i] = ray.o.z;
+        a.pool.dx[i] = ray.d.x; a.pool.dy[i] = ray.d.y; a.pool.dz[i] = ray.d.z;
+        a.pool.time[i] = ray.time;
+        a.pool.best_t[i] = best.t; a.pool.best_rec[i] = best.rec; a.pool.best_chain[i] = best.chain;
+        a.pool.thr_r[i] = pc.thr_r; a.pool.thr_g[i] = pc.thr_g; a.pool.thr_b[i] = pc.thr_b;
+        a.pool.rad_r[i] = pc.rad_r; a.pool.rad_g[i] = pc.rad_g; a.pool.rad_b[i] = pc.rad_b;
+        a.pool.pixel[i] = smp.pixel; a.pool.sample[i] = smp.sample;
+        a.pool.bounce[i] = bounce;
+    } else if (dirty) {
+        a.pool.bounce[i] = -1;
+    }
+    if (active_out) {
+        const unsigned am = __ballot_sync(FULL, fresh);
+        if (lane == 0 && am != 0) atomicAdd(active_out, (unsigned int)__popc(am));
+    }
+    if constexpr (kCount) {
+        uint32_t v = tally.n_med;
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+        if (lane == 0 && v) atomicAdd(&counters->medium_tests, (unsigned long long)v);
+        // (node / primitive counts of general medium boundaries are not attributed)
+    }
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(kWfBlock) wf_trace_kernel(SceneView sc, PathPool pool, int n_slots, unsigned long long* ray_count,
+                                                            Counters* counters) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t stack[kStackSize];
+    Tally<kCount> tally;
+    const bool act = i < n_slots && pool.bounce[i] >= 0;
+    if (act) {
+        RayD ray{mk(pool.ox[i], pool.oy[i], pool.oz[i]), mk(pool.dx[i], pool.dy[i], pool.dz[i]), pool.time[i]};
+        Best best{pool.best_t[i], -1, 0};
+        traverse_simple(sc, sc.world_root, ray, 0.001, best, stack, 0, tally);
+        if (best.rec >= 0) {  // closer than the medium candidate (if any) the shade kernel left there
+            pool.best_t[i] = best.t;
+            pool.best_rec[i] = best.rec;
+            pool.best_chain[i] = best.chain;
+        }
+    }
+    if (ray_count) {
+        const unsigned am = __ballot_sync(FULL, act);
+        if (lane == 0 && am != 0) atomicAdd(ray_count, (unsigned long long)__popc(am));
+    }
+    if constexpr (kCount) {
+        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
+        if (lane == 0) {
+            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
+            atomicAdd(&counters->box_tests, 2ull * vals[0]);
+            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
+            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
+            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
+        }
+    }
+}
+
+// color(.., depth = 0) is black without tracing anything (main.rs:27-29): count the samples only
+__global__ void add_black_samples_kernel(float4* __restrict__ accum, int n_pixels, float count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pixels) accum[i].w += count;
 }
 
 // ---------------------------------------------------------------------------
