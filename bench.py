@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=32, help="samples per pixel per rank per step")
+    ap.add_argument("--spp", type=int, default=128, help="samples per pixel per rank per step")
     ap.add_argument("--scene", type=int, default=SCENE)
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
@@ -325,7 +325,13 @@ def run_ours(args):
                 abi.check(real_lib.rtx_tonemap_rgba8(ctx.h, accum, w, h, C.c_void_p(d_rgba.data_ptr()), 1))
         else:
             abi.check(real_lib.rtx_reduce_tonemap_peers(ctx.h, accum, None, 0, w, h, C.c_void_p(d_rgba.data_ptr())))
+    ctx.set_profiling(True)  # CUDA events around every shade / trace launch, on the launching stream
+    ctx.profile_read(reset=True)
+    launches0 = ctx.kernel_launches()
     total_ms, clocks = timed(step_resident, args.steps, sample_clocks=True)
+    launches = ctx.kernel_launches() - launches0
+    prof = ctx.profile_read(reset=True)
+    ctx.set_profiling(False)
     kern_ms = [a.elapsed_time(b) for a, b in kev]
     rays_rank = int(ray_counter.item())
     samples_total = n_px * args.spp * world * args.steps
@@ -361,8 +367,11 @@ def run_ours(args):
         # A_ray = 32 B per child box tested + 32 B per primitive tested + 64 B per instance entered
         a_ray = 32.0 * st["box_tests"] + 32.0 * (st["sphere_tests"] + st["rect_tests"]) + 64.0 * st["instance_enters"]
         f_ray = 12.0 * st["box_tests"] + 30.0 * st["sphere_tests"] + 12.0 * st["rect_tests"] + 40.0 * st["instance_enters"]
-        kms = sum(kern_ms) / len(kern_ms)
-        rays_per_launch = rays_rank / args.steps
+        # the dominant kernel is the wavefront trace kernel: one launch per iteration, every ray of the step goes
+        # through exactly one of them
+        n_it = max(1, prof["iterations"])
+        kms = prof["trace_ms"] / n_it
+        rays_per_launch = rays_rank / n_it
         achieved = a_ray * rays_per_launch / (kms * 1e-3) / 1e9
         peaks = {}
         try:
@@ -372,24 +381,26 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get("render_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get("wf_trace_kernel_dram_bytes_per_launch")
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "render_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / total_ms,
+                    "kernel": "wf_trace_kernel", "kernel_ms_per_launch": kms, "launches_per_step": n_it / args.steps,
+                    "kernel_share_of_step": prof["trace_ms"] / total_ms, "shade_kernel_share_of_step": prof["shade_ms"] / total_ms,
+                    "render_call_ms_per_step": sum(kern_ms) / len(kern_ms),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_ray": a_ray, "algorithmic_flops_per_ray": f_ray, "rays_per_launch": rays_per_launch,
                     "per_ray_means": {k: st[k] for k in ("box_tests", "node_visits", "sphere_tests", "rect_tests", "instance_enters", "medium_tests")},
-                    "note": "the flattened scene (%.1f MB) is L2-resident: the algorithmic bytes are BVH-node and primitive bytes the "
-                            "traversal must fetch, served by L1/L2, so HBM is not what bounds this kernel; see profiles/ for "
-                            "issue-slot and L2 figures" % (info["device_bytes"] / 1e6)}
+                    "note": "the flattened scene (%.1f MB) and the path pool are L2-resident: the algorithmic bytes are the BVH-node and "
+                            "primitive bytes the traversal must fetch, served by L1/L2, so HBM is not what bounds this kernel "
+                            "(latency / issue slots are: see profiles/)" % (info["device_bytes"] / 1e6)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 geometry / f32 BVH boxes, shading and accumulation", "data": "synthetic",
                 "config": config(args, d, w, h, {"combine": combine, "bvh_nodes": info["bvh_nodes"], "records": info["records"],
                                                  "scene_bytes": info["device_bytes"]}),
                 "rays_per_sec": rays_total / (total_ms * 1e-3), "rays_per_sample": rays_total / samples_total,
-                "clocks": clocks, "gpu_launches": 2 * args.steps,
+                "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": n_px * 4,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
                 "roofline": roofline}

@@ -229,6 +229,15 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out);
 int rtx_ctx_destroy(rtx_ctx* ctx);
 int rtx_ctx_sync(rtx_ctx* ctx);
 void* rtx_ctx_stream(rtx_ctx* ctx);
+/* number of CUDA kernels this context has launched so far (bookkeeping for benchmarks) */
+int rtx_ctx_kernel_launches(rtx_ctx* ctx, unsigned long long* out);
+/* Per-kernel timing of rtx_render (benchmark bookkeeping): when on, every shade / trace launch is
+ * bracketed by CUDA events on the ctx stream and rtx_render waits for the last one before it
+ * returns. rtx_ctx_profile_read returns the accumulated device milliseconds of the two kernels and
+ * the number of (shade, trace) iterations they cover; reset != 0 clears the accumulators. */
+int rtx_ctx_set_profiling(rtx_ctx* ctx, int on);
+int rtx_ctx_profile_read(rtx_ctx* ctx, double* shade_ms, double* trace_ms,
+                         unsigned long long* iterations, int reset);
 
 /* ---- scene: flattens the tree, builds the BVHs, uploads (host memory is
  * copied; the caller keeps ownership of everything in `desc`). ---- */
@@ -252,7 +261,11 @@ int rtx_trace_rays_stats(rtx_ctx* ctx, const rtx_scene* scene, int64_t n, const 
 /* ---- render ---- */
 /* Adds spp_count samples per pixel into d_accum (device, width*height float4:
  * sum r, sum g, sum b, sample count; row 0 = TOP row, matching the order the
- * reference emits pixels, src/main.rs:202-204). Asynchronous on the ctx stream.
+ * reference emits pixels, src/main.rs:202-204). All work is ordered on the ctx
+ * stream and the result is NOT synchronised on return; the call itself may keep
+ * the calling thread busy while it feeds the stream (the wavefront driver polls
+ * a completion counter). Samples are added with atomics: the fp32 summation
+ * order, hence the last bits of the sums, can differ from run to run.
  * d_ray_count (device uint64, may be NULL) is incremented by the number of
  * world.hit queries issued. */
 int rtx_render(rtx_ctx* ctx, const rtx_scene* scene, const rtx_render_params* params,

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librttnw_b200.so")
+# RTTNW_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("RTTNW_B200_LIB") or os.path.join(_HERE, "lib", "librttnw_b200.so")
 
 RTX_OK = 0
 RTX_MISS = -1
@@ -109,6 +110,9 @@ SIGNATURES = {
     "rtx_ctx_destroy": (C.c_int, [_P]),
     "rtx_ctx_sync": (C.c_int, [_P]),
     "rtx_ctx_stream": (_P, [_P]),
+    "rtx_ctx_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "rtx_ctx_set_profiling": (C.c_int, [_P, C.c_int]),
+    "rtx_ctx_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "rtx_scene_create": (C.c_int, [_P, C.POINTER(SceneDesc), C.POINTER(_P)]),
     "rtx_scene_destroy": (C.c_int, [_P]),
     "rtx_scene_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),

@@ -45,12 +45,21 @@ struct rtx_ctx {
     int mode = 1;  // 1: wavefront (default), 0: megakernel (RTX_MODE=mega)
     // wavefront state, allocated at the first render
     void* d_pool = nullptr;
-    int pool_slots = 0, pool_slots_wanted = 1 << 20;
+    int pool_slots = 0, pool_slots_wanted = 1 << 19;  // 512 Ki slots x 108 B = 54 MB: stays in the 126 MB L2
     unsigned long long* d_next_item = nullptr;
     unsigned int* d_active = nullptr;            // [2]
     unsigned long long* h_status = nullptr;      // pinned: [2][2] = {active, next_item} per batch parity
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
     int wf_batch = 8;
+    int wf_trace = 0;  // 0: one slot per thread (default), 1: persistent vote-batched (RTX_WF_TRACE=vote), 2: persistent refill (=refill)
+    unsigned long long launches = 0;  // kernels launched by this context (rtx_ctx_kernel_launches)
+    // optional per-kernel timing of the wavefront driver (rtx_ctx_set_profiling): CUDA events around every launch
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // grows on demand; [4 * iteration + {0,1,2,3}] = shade begin/end, trace begin/end
+    double prof_shade_ms = 0, prof_trace_ms = 0;
+    unsigned long long prof_iterations = 0;
+    unsigned int* d_next_slot = nullptr;  // [wf_batch] per-iteration slot counters of the persistent trace kernel
+    int trace_grid = 0;
     int w_node = 1, w_leaf = 1, w_shade = 1;  // render_kernel phase weights (RTX_W_NODE / RTX_W_LEAF / RTX_W_SHADE override)
 };
 
@@ -113,6 +122,7 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->pool_slots_wanted = env_int("RTX_WF_SLOTS", c->pool_slots_wanted);
     c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
+    if (const char* m = std::getenv("RTX_WF_TRACE")) c->wf_trace = std::strcmp(m, "vote") == 0 ? 1 : (std::strcmp(m, "refill") == 0 ? 2 : 0);
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -129,9 +139,11 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     cudaFree(c->d_pool);
     cudaFree(c->d_next_item);
     cudaFree(c->d_active);
+    cudaFree(c->d_next_slot);
     if (c->h_status) cudaFreeHost(c->h_status);
     for (auto& e : c->batch_done)
         if (e) cudaEventDestroy(e);
+    for (auto e : c->prof_events) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTX_OK;
@@ -144,6 +156,24 @@ int rtx_ctx_sync(rtx_ctx* c) {
     return RTX_OK;
 }
 void* rtx_ctx_stream(rtx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int rtx_ctx_set_profiling(rtx_ctx* c, int on) {
+    if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    c->profiling = on != 0;
+    return RTX_OK;
+}
+int rtx_ctx_profile_read(rtx_ctx* c, double* shade_ms, double* trace_ms, unsigned long long* iterations, int reset) {
+    if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    if (shade_ms) *shade_ms = c->prof_shade_ms;
+    if (trace_ms) *trace_ms = c->prof_trace_ms;
+    if (iterations) *iterations = c->prof_iterations;
+    if (reset) { c->prof_shade_ms = c->prof_trace_ms = 0; c->prof_iterations = 0; }
+    return RTX_OK;
+}
+int rtx_ctx_kernel_launches(rtx_ctx* c, unsigned long long* out) {
+    if (!c || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    *out = c->launches;
+    return RTX_OK;
+}
 
 // ---- scene ----------------------------------------------------------------
 int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
@@ -268,6 +298,7 @@ int rtx_trace_rays_device(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_r
     int64_t grid = (n + block - 1) / block;
     if (grid > 0x7fffffff) return fail(RTX_ERR_INVALID, "too many rays for one launch");
     rtx::trace_rays_kernel<false><<<(unsigned)grid, block, 0, c->stream>>>(s->view, n, d_rays, d_hits, nullptr);
+    c->launches += 1;
     CU(cudaGetLastError());
     return RTX_OK;
 }
@@ -305,6 +336,7 @@ int rtx_trace_rays_stats(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ra
     int64_t grid = (n + block - 1) / block;
     if (grid > 0x7fffffff) return fail(RTX_ERR_INVALID, "too many rays for one launch");
     rtx::trace_rays_kernel<true><<<(unsigned)grid, block, 0, c->stream>>>(s->view, n, d_rays, nullptr, c->d_counters);
+    c->launches += 1;
     CU(cudaGetLastError());
     rtx::Counters h;
     CU(cudaMemcpyAsync(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -329,6 +361,12 @@ static int wf_prepare(rtx_ctx* c, int64_t slots) {
     }
     if (!c->d_next_item) CU(cudaMalloc(&c->d_next_item, sizeof(unsigned long long)));
     if (!c->d_active) CU(cudaMalloc(&c->d_active, 2 * sizeof(unsigned int)));
+    if (!c->d_next_slot) {
+        CU(cudaMalloc(&c->d_next_slot, (size_t)c->wf_batch * sizeof(unsigned int)));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::wf_trace_persistent_kernel<false>, rtx::kWfBlock, 0));
+        c->trace_grid = c->sm_count * (per_sm < 1 ? 1 : per_sm);
+    }
     if (!c->h_status) CU(cudaMallocHost(&c->h_status, 4 * sizeof(unsigned long long)));
     for (auto& e : c->batch_done)
         if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -378,23 +416,57 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     float4* acc = reinterpret_cast<float4*>(d_accum);
     const unsigned grid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
     const int batch = c->wf_batch;
+    rtx::TraceTune tune{c->w_node, c->w_leaf, c->w_shade, c->node_burst, std::getenv("RTX_SPECULATE") ? 1 : 0};
+    unsigned tgrid = (unsigned)c->trace_grid;
+    if ((int64_t)tgrid * (rtx::kWfBlock / 32) * 32 > slots) tgrid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
+    size_t prof_used = 0;
+    auto prof_mark = [&](void) -> cudaError_t {
+        if (!c->profiling) return cudaSuccess;
+        if (prof_used == c->prof_events.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            c->prof_events.push_back(e);
+        }
+        return cudaEventRecord(c->prof_events[prof_used++], c->stream);
+    };
     for (int k = 0;; ++k) {
         const int par = k & 1;
+        if (c->wf_trace) CU(cudaMemsetAsync(c->d_next_slot, 0, (size_t)batch * sizeof(unsigned int), c->stream));
         for (int it = 0; it < batch; ++it) {
             unsigned int* active = nullptr;
             if (it == batch - 1) {
                 active = c->d_active + par;
                 CU(cudaMemsetAsync(active, 0, sizeof(unsigned int), c->stream));
             }
+            CU(prof_mark());
             if (counted) {
                 rtx::wf_shade_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
-                rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
+                CU(prof_mark());
+                CU(prof_mark());
+                if (c->wf_trace == 2)
+                    rtx::wf_trace_refill_kernel<true><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, d_ray_count, c->d_counters);
+                else if (c->wf_trace)
+                    rtx::wf_trace_persistent_kernel<true><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, tune,
+                                                                                                 d_ray_count, c->d_counters);
+                else
+                    rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
             } else {
                 rtx::wf_shade_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, nullptr);
-                rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);
+                CU(prof_mark());
+                CU(prof_mark());
+                if (c->wf_trace == 2)
+                    rtx::wf_trace_refill_kernel<false><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, d_ray_count, nullptr);
+                else if (c->wf_trace)
+                    rtx::wf_trace_persistent_kernel<false><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, tune,
+                                                                                                  d_ray_count, nullptr);
+                else
+                    rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);
             }
+            CU(prof_mark());
         }
         CU(cudaGetLastError());
+        c->launches += 2ull * (unsigned long long)batch;
         // status of this batch -> pinned memory (active is 32-bit: widen on the host side)
         c->h_status[2 * par] = 0;
         CU(cudaMemcpyAsync(&c->h_status[2 * par], c->d_active + par, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
@@ -408,6 +480,17 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     }
     // the batch queued behind the one that ended dry runs over empty slots only; later calls on this
     // stream are ordered after it
+    if (c->profiling && prof_used >= 4) {
+        CU(cudaEventSynchronize(c->prof_events[prof_used - 1]));
+        for (size_t q = 0; q + 3 < prof_used; q += 4) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->prof_events[q], c->prof_events[q + 1]));
+            c->prof_shade_ms += ms;
+            CU(cudaEventElapsedTime(&ms, c->prof_events[q + 2], c->prof_events[q + 3]));
+            c->prof_trace_ms += ms;
+            c->prof_iterations += 1;
+        }
+    }
     return RTX_OK;
 }
 
@@ -424,6 +507,7 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     if (p->max_depth == 0) {  // color(.., depth = 0) is black (main.rs:27-29): only the sample counts move
         int n = p->width * p->height;
         rtx::add_black_samples_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<float4*>(d_accum), n, (float)p->spp_count);
+        c->launches += 1;
         CU(cudaGetLastError());
         return RTX_OK;
     }
@@ -456,6 +540,7 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     else
         rtx::render_kernel<false><<<(unsigned)grid, rtx::kRenderBlock, 0, c->stream>>>(a, acc, d_ray_count, c->d_work_counter, nullptr);
     CU(cudaGetLastError());
+    c->launches += 1;
     return RTX_OK;
 }
 
@@ -499,6 +584,7 @@ int rtx_tonemap_rgba8(rtx_ctx* c, const float* d_accum, int32_t width, int32_t h
     uchar4* d_out = (uchar4*)out;
     if (!out_on_device) CU(cudaMalloc(&d_out, (size_t)n * 4));
     rtx::tonemap_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(d_accum), n, d_out);
+    c->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (!out_on_device) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
@@ -533,6 +619,7 @@ int rtx_reduce_tonemap_peers(rtx_ctx* c, float* d_accum, const float* const* d_p
     rtx::reduce_tonemap_peers_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<float4*>(d_accum), pl, n,
                                                                             reinterpret_cast<uchar4*>(d_rgba8));
     CU(cudaGetLastError());
+    c->launches += 1;
     return RTX_OK;
 }
 

@@ -1037,9 +1037,15 @@ struct WfArgs {
 };
 
 constexpr int kWfBlock = 128;
+#ifndef WF_TRACE_MINB
+#define WF_TRACE_MINB 8
+#endif
+#ifndef WF_SHADE_MINB
+#define WF_SHADE_MINB 5
+#endif
 
 template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
+__global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1129,7 +1135,7 @@ __global__ void __launch_bounds__(kWfBlock) wf_shade_kernel(WfArgs a, float4* __
 }
 
 template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock) wf_trace_kernel(SceneView sc, PathPool pool, int n_slots, unsigned long long* ray_count,
+__global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_kernel(SceneView sc, PathPool pool, int n_slots, unsigned long long* ray_count,
                                                             Counters* counters) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1150,6 +1156,299 @@ __global__ void __launch_bounds__(kWfBlock) wf_trace_kernel(SceneView sc, PathPo
     if (ray_count) {
         const unsigned am = __ballot_sync(FULL, act);
         if (lane == 0 && am != 0) atomicAdd(ray_count, (unsigned long long)__popc(am));
+    }
+    if constexpr (kCount) {
+        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
+        if (lane == 0) {
+            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
+            atomicAdd(&counters->box_tests, 2ull * vals[0]);
+            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
+            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
+            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
+        }
+    }
+}
+
+// Persistent form of the trace kernel: a warp keeps 32 rays in flight and a lane whose ray is done
+// writes its hit and takes the next slot from a global counter, so a long ray no longer holds 31
+// idle lanes (the one-slot-per-thread form runs at ~9 of 32 lanes: a warp lasts as long as its
+// longest ray). Three kinds of steps — BVH node steps (fp32), leaf events (f64 tests, instance
+// enter / leave) and fetches (write back, load the next ray, slab set-up) — are run one kind at a
+// time for all lanes waiting for that kind, chosen by vote; a lane that reaches a leaf postpones it
+// and keeps traversing speculatively.
+struct TraceTune {
+    int32_t w_node, w_leaf, w_fetch;  // vote weights
+    int32_t node_burst;               // node steps per vote, at most
+    int32_t speculate;                // 1: keep traversing with one leaf postponed
+};
+
+template <bool kCount>
+__global__ void __launch_bounds__(kWfBlock) wf_trace_persistent_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
+                                                                       TraceTune tune, unsigned long long* ray_count, Counters* counters) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int32_t stack[kStackSize];
+    Tally<kCount> tally;
+    const float tmin_f = __double2float_rd(0.001);
+    // lane state: slot < 0 = no ray (wants a fetch); dry = the counter ran past n_slots
+    int slot = -1;
+    bool dry = false;
+    RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
+    SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Best best{0.0, -1, 0};
+    float tmax_f = 0.f;
+    int32_t cur = kSentinel, pending = 0, cur_chain = 0;
+    int sp = 0;
+    unsigned int my_rays = 0;
+
+    while (true) {
+        // ---- cheap per-lane transitions, then the vote ----
+        bool finished = false;
+        if (slot >= 0 && cur < 0) {
+            if (cur == kSentinel) {
+                finished = pending == 0;
+            } else if (cur != kLeaveInstance && pending == 0) {
+                pending = cur;  // postpone the leaf, keep traversing (speculatively: best.t is not shrunk yet)
+                cur = stack[--sp];
+            }
+        }
+        // (without speculation a postponed leaf is tested before the lane takes another node step: the first
+        // leaf along an ordered traversal is usually the closest hit and prunes most of what is left)
+        const bool want_node = slot >= 0 && cur >= 0 && (pending == 0 || tune.speculate != 0);
+        const bool want_leaf = slot >= 0 && !want_node && (pending != 0 || cur == kLeaveInstance);
+        const bool want_fetch = (slot < 0 && !dry) || finished;
+        const int n_node = __popc(__ballot_sync(FULL, want_node));
+        const int n_leaf = __popc(__ballot_sync(FULL, want_leaf));
+        const int n_fetch = __popc(__ballot_sync(FULL, want_fetch));
+        if ((n_node | n_leaf | n_fetch) == 0) break;  // every lane is dry and idle
+        const int s_node = n_node * tune.w_node, s_leaf = n_leaf * tune.w_leaf, s_fetch = n_fetch * tune.w_fetch;
+
+        if (s_node >= s_leaf && s_node >= s_fetch) {
+            // ================= node phase =================
+            bool go = want_node;
+#pragma unroll 1
+            for (int it = 0; it < tune.node_burst; ++it) {
+                if (go) {
+                    cur = node_step(sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
+                    if (cur < 0 && cur != kSentinel && cur != kLeaveInstance && pending == 0) {
+                        pending = cur;
+                        cur = stack[--sp];
+                    }
+                    go = cur >= 0 && (pending == 0 || tune.speculate != 0);
+                }
+                if (2 * __popc(__ballot_sync(FULL, go)) < n_node) break;
+            }
+        } else if (s_leaf >= s_fetch) {
+            // ================= leaf phase =================
+            if (want_leaf) {
+                d3 o = ray.o, d = ray.d;
+                bool reslab = false;
+                if (pending != 0) {
+                    if (cur_chain != 0) to_space(sc, cur_chain, o, d);
+                    int32_t v = ~pending;
+                    int32_t first = v >> 4, count = v & 15;
+                    pending = 0;
+                    for (int32_t i = 0; i < count; ++i) {
+                        const Record* rp = sc.records + first + i;
+                        int4 h = __ldg(reinterpret_cast<const int4*>(rp));
+                        if (h.x == REC_INSTANCE) {  // Translate / YRotate::hit: re-express the ray, descend
+                            tally.instance();
+                            cur_chain = h.w;
+                            o = ray.o; d = ray.d;
+                            to_space(sc, cur_chain, o, d);
+                            reslab = true;
+                            stack[sp++] = cur;
+                            stack[sp++] = kLeaveInstance;
+                            cur = h.y;
+                        } else if (h.x <= REC_RECT_YZ) {
+                            double t;
+                            if (test_geometry(rp, h.x, o, d, ray.time, 0.001, best.t, t, tally)) {
+                                best.t = t;
+                                best.rec = first + i;
+                                best.chain = cur_chain;
+                                tmax_f = __double2float_ru(t);
+                            }
+                        }
+                    }
+                }
+                if (cur == kLeaveInstance) {  // back to world space
+                    o = ray.o; d = ray.d;
+                    reslab = true;
+                    cur_chain = 0;
+                    cur = stack[--sp];
+                }
+                if (reslab) make_slab(o, d, sr);
+            }
+        } else {
+            // ================= fetch phase =================
+            if (finished) {
+                if (best.rec >= 0) {  // closer than the medium candidate (if any) the shade kernel left there
+                    pool.best_t[slot] = best.t;
+                    pool.best_rec[slot] = best.rec;
+                    pool.best_chain[slot] = best.chain;
+                }
+                slot = -1;
+            }
+            // take slots until every fetching lane has an occupied one (or the counter runs dry)
+            unsigned need = __ballot_sync(FULL, want_fetch);
+            while (need != 0) {
+                const int leader = __ffs(need) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(next_slot, (unsigned int)__popc(need));
+                base = __shfl_sync(FULL, base, leader);
+                const bool mine = ((need >> lane) & 1u) != 0;
+                if (mine) {
+                    const unsigned int idx = base + (unsigned int)__popc(need & lt_mask);
+                    if (idx >= (unsigned int)n_slots) {
+                        dry = true;
+                    } else if (pool.bounce[idx] >= 0) {
+                        slot = (int)idx;
+                    }
+                }
+                need = __ballot_sync(FULL, mine && slot < 0 && !dry);
+            }
+            if (want_fetch && slot >= 0) {
+                ray.o = mk(pool.ox[slot], pool.oy[slot], pool.oz[slot]);
+                ray.d = mk(pool.dx[slot], pool.dy[slot], pool.dz[slot]);
+                ray.time = pool.time[slot];
+                best.t = pool.best_t[slot];
+                best.rec = -1;
+                best.chain = 0;
+                make_slab(ray.o, ray.d, sr);
+                tmax_f = __double2float_ru(best.t);
+                sp = 0;
+                stack[sp++] = kSentinel;
+                cur = sc.world_root;
+                pending = 0;
+                cur_chain = 0;
+                ++my_rays;
+            }
+        }
+    }
+    if (ray_count) {
+        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(FULL, my_rays, off);
+        if (lane == 0 && my_rays) atomicAdd(ray_count, (unsigned long long)my_rays);
+    }
+    if constexpr (kCount) {
+        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
+        if (lane == 0) {
+            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
+            atomicAdd(&counters->box_tests, 2ull * vals[0]);
+            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
+            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
+            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
+        }
+    }
+}
+
+// Persistent while-while form: lanes refill at the top of the loop (one warp-aggregated atomic), then
+// every lane walks down to its next leaf on its own and tests it. No votes inside the walk.
+template <bool kCount>
+__global__ void __launch_bounds__(kWfBlock) wf_trace_refill_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
+                                                                   unsigned long long* ray_count, Counters* counters) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int32_t stack[kStackSize];
+    Tally<kCount> tally;
+    const float tmin_f = __double2float_rd(0.001);
+    int slot = -1;
+    bool dry = false;
+    RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
+    d3 o = ray.o, d = ray.d;  // the ray in the space being traversed
+    SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Best best{0.0, -1, 0};
+    float tmax_f = 0.f;
+    int32_t cur = kSentinel, cur_chain = 0;
+    int sp = 0;
+    unsigned int my_rays = 0;
+    while (true) {
+        // ---- refill ----
+        unsigned need = __ballot_sync(FULL, slot < 0 && !dry);
+        const bool fetching = ((need >> lane) & 1u) != 0;
+        while (need != 0) {
+            const int leader = __ffs(need) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(next_slot, (unsigned int)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            const bool mine = ((need >> lane) & 1u) != 0;
+            if (mine) {
+                const unsigned int idx = base + (unsigned int)__popc(need & lt_mask);
+                if (idx >= (unsigned int)n_slots) dry = true;
+                else if (pool.bounce[idx] >= 0) slot = (int)idx;
+            }
+            need = __ballot_sync(FULL, mine && slot < 0 && !dry);
+        }
+        if (fetching && slot >= 0) {
+            ray.o = mk(pool.ox[slot], pool.oy[slot], pool.oz[slot]);
+            ray.d = mk(pool.dx[slot], pool.dy[slot], pool.dz[slot]);
+            ray.time = pool.time[slot];
+            o = ray.o; d = ray.d;
+            best.t = pool.best_t[slot];
+            best.rec = -1;
+            best.chain = 0;
+            make_slab(o, d, sr);
+            tmax_f = __double2float_ru(best.t);
+            sp = 0;
+            stack[sp++] = kSentinel;
+            cur = sc.world_root;
+            cur_chain = 0;
+            ++my_rays;
+        }
+        if (__all_sync(FULL, slot < 0)) break;
+        if (slot >= 0) {
+            while (cur >= 0) cur = node_step(sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
+            if (cur == kSentinel) {
+                if (best.rec >= 0) {
+                    pool.best_t[slot] = best.t;
+                    pool.best_rec[slot] = best.rec;
+                    pool.best_chain[slot] = best.chain;
+                }
+                slot = -1;
+            } else if (cur == kLeaveInstance) {
+                o = ray.o; d = ray.d;
+                make_slab(o, d, sr);
+                cur_chain = 0;
+                cur = stack[--sp];
+            } else {
+                int32_t v = ~cur;
+                int32_t first = v >> 4, count = v & 15;
+                cur = stack[--sp];
+                for (int32_t i = 0; i < count; ++i) {
+                    const Record* rp = sc.records + first + i;
+                    int4 h = __ldg(reinterpret_cast<const int4*>(rp));
+                    if (h.x == REC_INSTANCE) {
+                        tally.instance();
+                        cur_chain = h.w;
+                        o = ray.o; d = ray.d;
+                        to_space(sc, cur_chain, o, d);
+                        make_slab(o, d, sr);
+                        stack[sp++] = cur;
+                        stack[sp++] = kLeaveInstance;
+                        cur = h.y;
+                    } else if (h.x <= REC_RECT_YZ) {
+                        double t;
+                        if (test_geometry(rp, h.x, o, d, ray.time, 0.001, best.t, t, tally)) {
+                            best.t = t;
+                            best.rec = first + i;
+                            best.chain = cur_chain;
+                            tmax_f = __double2float_ru(t);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (ray_count) {
+        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(FULL, my_rays, off);
+        if (lane == 0 && my_rays) atomicAdd(ray_count, (unsigned long long)my_rays);
     }
     if constexpr (kCount) {
         uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};

@@ -96,6 +96,19 @@ class Context:
     def sync(self) -> None:
         abi.check(self.lib.rtx_ctx_sync(self.h))
 
+    def set_profiling(self, on: bool) -> None:
+        abi.check(self.lib.rtx_ctx_set_profiling(self.h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
+        abi.check(self.lib.rtx_ctx_profile_read(self.h, C.byref(a), C.byref(b), C.byref(n), 1 if reset else 0))
+        return {"shade_ms": a.value, "trace_ms": b.value, "iterations": n.value}
+
+    def kernel_launches(self) -> int:
+        n = C.c_uint64()
+        abi.check(self.lib.rtx_ctx_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
     def close(self) -> None:
         if self.h:
             self.lib.rtx_ctx_destroy(self.h)
