@@ -370,7 +370,7 @@ def run_ours(args):
         # the dominant kernel is the wavefront trace kernel: one launch per iteration, every ray of the step goes
         # through exactly one of them
         n_it = max(1, prof["iterations"])
-        kms = prof["trace_ms"] / n_it
+        kms = prof["trace_ms"] / n_it if prof["iterations"] else sum(kern_ms) / len(kern_ms)  # (megakernel mode: one launch per step)
         rays_per_launch = rays_rank / n_it
         achieved = a_ray * rays_per_launch / (kms * 1e-3) / 1e9
         peaks = {}
@@ -385,8 +385,8 @@ def run_ours(args):
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "wf_trace_kernel", "kernel_ms_per_launch": kms, "launches_per_step": n_it / args.steps,
-                    "kernel_share_of_step": prof["trace_ms"] / total_ms, "shade_kernel_share_of_step": prof["shade_ms"] / total_ms,
+                    "kernel": "wf_trace_kernel" if prof["iterations"] else "render_kernel", "kernel_ms_per_launch": kms, "launches_per_step": n_it / args.steps,
+                    "kernel_share_of_step": (prof["trace_ms"] if prof["iterations"] else sum(kern_ms)) / total_ms, "shade_kernel_share_of_step": prof["shade_ms"] / total_ms,
                     "render_call_ms_per_step": sum(kern_ms) / len(kern_ms),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_ray": a_ray, "algorithmic_flops_per_ray": f_ray, "rays_per_launch": rays_per_launch,

@@ -1186,7 +1186,7 @@ struct TraceTune {
 };
 
 template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock) wf_trace_persistent_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
+__global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_persistent_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
                                                                        TraceTune tune, unsigned long long* ray_count, Counters* counters) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1351,7 +1351,7 @@ __global__ void __launch_bounds__(kWfBlock) wf_trace_persistent_kernel(SceneView
 // Persistent while-while form: lanes refill at the top of the loop (one warp-aggregated atomic), then
 // every lane walks down to its next leaf on its own and tests it. No votes inside the walk.
 template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock) wf_trace_refill_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
+__global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_refill_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
                                                                    unsigned long long* ray_count, Counters* counters) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
