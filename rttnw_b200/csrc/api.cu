@@ -384,7 +384,8 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     const int64_t n_tiles = (int64_t)((p->width + rtx::kTileW - 1) / rtx::kTileW) * ((p->height + rtx::kTileH - 1) / rtx::kTileH);
     const unsigned long long total = (unsigned long long)n_tiles * 32ull * (unsigned long long)p->spp_count;
     int64_t slots = c->pool_slots_wanted;
-    if ((unsigned long long)slots > total) slots = (int64_t)((total + 127) / 128 * 128);
+    if ((unsigned long long)slots > total) slots = (int64_t)total;
+    slots = (slots + rtx::kWfBlock - 1) / rtx::kWfBlock * rtx::kWfBlock;  // whole CTAs
     int rc = wf_prepare(c, slots);
     if (rc != RTX_OK) return rc;
     rtx::WfArgs a;

@@ -27,8 +27,9 @@ enum RecType : int32_t {
     REC_RECT_XZ = 3,   //                                                   (0,2,1)
     REC_RECT_YZ = 4,   //                                                   (1,2,0)
     REC_INSTANCE = 5,  // a = BVH root of the instanced group, c = chain index (SceneView::chains)
-    REC_MEDIUM = 6     // a = phase texture, b = prim id, c = boundary BVH root (or -1: the boundary is
-                       // the untransformed sphere d[4..7] = {cx, cy, cz, r});
+    REC_MEDIUM = 6     // a = phase texture, b = prim id, c = boundary BVH root, or -1: the boundary is the
+                       // untransformed sphere d[4..7] = {cx, cy, cz, r}, or <= -2: it is the box
+                       // d[4..9] = {lo, hi} in the space of chain (-2 - c);
                        // d = {neg_inv_density, medium ordinal, outer chain index}.
                        // Medium records are not BVH leaves: they are listed in SceneView::media.
 };

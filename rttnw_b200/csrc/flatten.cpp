@@ -290,6 +290,25 @@ struct Flattener {
 
     bool check_material(int m) { return m >= 0 && m < d.n_materials; }
 
+    // Are these exactly the six rectangles Cube::new makes for one box with lo < hi on every axis?
+    static bool is_cube(const std::vector<Item>& items, double lo[3], double hi[3]) {
+        if (items.size() != 6) return false;
+        static const int planes[6] = {0, 0, 1, 1, 2, 2};
+        for (int i = 0; i < 6; ++i)
+            if (items[(size_t)i].rec.type != REC_RECT_XY + planes[i]) return false;
+        const double* r0 = items[0].rec.d;
+        lo[0] = r0[0]; hi[0] = r0[1]; lo[1] = r0[2]; hi[1] = r0[3]; lo[2] = r0[4]; hi[2] = items[1].rec.d[4];
+        for (int i = 0; i < 3; ++i)
+            if (!(lo[i] < hi[i])) return false;
+        const double want[6][5] = {{lo[0], hi[0], lo[1], hi[1], lo[2]}, {lo[0], hi[0], lo[1], hi[1], hi[2]},
+                                   {lo[0], hi[0], lo[2], hi[2], lo[1]}, {lo[0], hi[0], lo[2], hi[2], hi[1]},
+                                   {lo[1], hi[1], lo[2], hi[2], lo[0]}, {lo[1], hi[1], lo[2], hi[2], hi[0]}};
+        for (int i = 0; i < 6; ++i)
+            for (int k = 0; k < 5; ++k)
+                if (items[(size_t)i].rec.d[k] != want[i][k]) return false;
+        return true;
+    }
+
     bool collect(int ni, std::vector<int>& path, std::vector<XformOp>& chain, World& w, int depth) {
         if (ni < 0 || ni >= d.n_nodes) return fail("node index out of range");
         if (depth > 256) return fail("scene tree deeper than 256 (cycle?)");
@@ -397,11 +416,30 @@ struct Flattener {
                 std::memset(&it.rec, 0, sizeof(it.rec));
                 // The common case (scenes.rs:282-301): the boundary is one untransformed Sphere. Its two
                 // boundary.hit() calls (hittable.rs:745-752) then reduce to the two roots of one quadratic.
-                const Group* only = (bw.paths.size() == 1 && bw.paths[0].empty() && bw.media.empty()) ? &bw.groups[bw.paths[0]] : nullptr;
+                const Group* only = (bw.paths.size() == 1 && bw.media.empty()) ? &bw.groups[bw.paths[0]] : nullptr;
                 int32_t root = -1;
-                if (only && only->items.size() == 1 && only->items[0].rec.type == REC_SPHERE && chain.empty()) {
+                double box_lo[3], box_hi[3];
+                if (only && only->chain.empty() && only->items.size() == 1 && only->items[0].rec.type == REC_SPHERE) {
                     for (int i = 0; i < 4; ++i) it.rec.d[4 + i] = only->items[0].rec.d[i];
                     bounds = only->items[0].box;
+                } else if (only && is_cube(only->items, box_lo, box_hi)) {
+                    // The other shipped case (scenes.rs:213-233): the boundary is one Cube, possibly under
+                    // Translate / YRotate wrappers. A line meets the six rectangles of a box exactly where it
+                    // enters and where it leaves, so the two boundary.hit() calls are one f64 slab computation
+                    // in the cube's own space: c = -2 - chain index.
+                    root = -2 - add_chain(only->chain);
+                    for (int i = 0; i < 3; ++i) { it.rec.d[4 + i] = box_lo[i]; it.rec.d[7 + i] = box_hi[i]; }
+                    bounds.reset();
+                    for (int corner = 0; corner < 8; ++corner) {
+                        double p[3] = {(corner & 1) ? box_hi[0] : box_lo[0], (corner & 2) ? box_hi[1] : box_lo[1],
+                                       (corner & 4) ? box_hi[2] : box_lo[2]};
+                        to_world(only->chain, p);
+                        bounds.grow_point(p);
+                    }
+                    for (int i = 0; i < 3; ++i) {
+                        double pad = 1e-4 + 1e-12 * std::fmax(1.0, std::fmax(std::fabs(bounds.lo[i]), std::fabs(bounds.hi[i])));
+                        bounds.lo[i] -= pad; bounds.hi[i] += pad;
+                    }
                 } else {
                     root = build_world(bw, bounds);
                 }

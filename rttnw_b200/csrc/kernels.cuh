@@ -320,7 +320,7 @@ __device__ __forceinline__ bool medium_candidate(const SceneView& sc, int32_t ri
     const double* q = rp->d;
     tally.medium();
     double r1, r2;
-    if (h.w < 0) {
+    if (h.w == -1) {
         // boundary = one untransformed sphere: hit(-inf, inf) is the near root, hit(t1 + 1e-4, inf) the far
         // root if it clears t1 + 1e-4 (Sphere::hit tries the near root first; it is below the new t_min)
         d3 c = mk(ldg_d(q + 4), ldg_d(q + 5), ldg_d(q + 6));
@@ -334,6 +334,21 @@ __device__ __forceinline__ bool medium_candidate(const SceneView& sc, int32_t ri
         r1 = (-half_b - sq) * inv_a;
         r2 = (-half_b + sq) * inv_a;
         if (r2 < r1 + 0.0001) return false;
+    } else if (h.w <= -2) {
+        // boundary = one Cube under a wrapper chain: the line meets its six rectangles where it enters and
+        // where it leaves the box, at the same (k - o) / d each Rectangle::hit computes (hittable.rs:504)
+        d3 o = ray.o, dd = ray.d;
+        if (h.w != -2) to_space(sc, -2 - h.w, o, dd);
+        r1 = -CUDART_INF;
+        r2 = CUDART_INF;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            double oa = comp(o, ax), da = comp(dd, ax);
+            double t0 = (ldg_d(q + 4 + ax) - oa) / da, t1 = (ldg_d(q + 7 + ax) - oa) / da;
+            r1 = fmax(r1, fmin(t0, t1));
+            r2 = fmin(r2, fmax(t0, t1));
+        }
+        if (!(r1 < r2) || r2 < r1 + 0.0001) return false;
     } else {
         // boundary.hit(ray, -inf, inf) then boundary.hit(ray, t1 + 1e-4, inf), hittable.rs:745-752
         r1 = r2 = 0.0;
@@ -453,7 +468,12 @@ __device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ra
                 c = mk(c.x + f * r, c.y + f * ldg_d(d + 4), c.z + f * ldg_d(d + 5));
                 r = ldg_d(d + 6);
             }
-            outward = mk((p.x - c.x) / r, (p.y - c.y) / r, (p.z - c.z) / r);  // hittable.rs:111,219
+            if (kPrecise) {
+                outward = mk((p.x - c.x) / r, (p.y - c.y) / r, (p.z - c.z) / r);  // hittable.rs:111,219
+            } else {  // render path: one reciprocal (differs from the three divisions by one rounding)
+                double ir = 1.0 / r;
+                outward = mk((p.x - c.x) * ir, (p.y - c.y) * ir, (p.z - c.z) * ir);
+            }
             if (kPrecise && h.x == REC_SPHERE) sphere_uv(outward, out.u, out.v);
         } else {
             int plane = h.x - REC_RECT_XY;
@@ -1044,19 +1064,38 @@ constexpr int kWfBlock = 128;
 #define WF_SHADE_MINB 5
 #endif
 
+// Three passes per CTA so that each piece of code runs on full warps:
+//   1. every thread shades the hit of its own slot (one level of color()); finished paths add their
+//      sample to the image and put the slot on a shared-memory list;
+//   2. the first ceil(Q / 32) warps generate the Q new camera rays densely (one dispenser atomic per
+//      CTA; consecutive items = the pixels of one 8x4 tile at one sample index) and hand each to the
+//      thread that owns the slot through shared memory;
+//   3. every thread that now has a ray — scattered or new — runs the medium pre-pass and writes its slot.
 template <bool kCount>
 __global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < a.n_slots;
+    __shared__ int s_queue[kWfBlock];
+    __shared__ int s_count;
+    __shared__ unsigned long long s_base;
+    __shared__ double s_ray[7][kWfBlock];
+    __shared__ uint32_t s_pix[2][kWfBlock];
+    __shared__ unsigned char s_staged[kWfBlock];
     int32_t stack[kStackSize];  // only a ConstantMedium with a general boundary traverses here
     Tally<kCount> tally;
+    if (tid == 0) s_count = 0;
+    s_staged[tid] = 0;
+    __syncthreads();
+
+    // ---- pass 1: shade ----
     int bounce = valid ? a.pool.bounce[i] : -2;
     RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
     PathColor pc{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
     Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
-    bool fresh = false, dirty = false;
+    bool fresh = false;
     if (bounce >= 0) {
         ray.o = mk(a.pool.ox[i], a.pool.oy[i], a.pool.oz[i]);
         ray.d = mk(a.pool.dx[i], a.pool.dy[i], a.pool.dz[i]);
@@ -1069,41 +1108,62 @@ __global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArg
         if (shade_hit(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce)) {
             atomicAdd(accum + smp.pixel, make_float4(pc.rad_r, pc.rad_g, pc.rad_b, 1.0f));  // one path sample done
             bounce = -1;
-            dirty = true;
+            a.pool.bounce[i] = -1;
         } else {
             fresh = true;
         }
     }
-    // ---- refill empty slots: consecutive items are the 32 pixels of one tile at one sample index ----
-    const bool want = bounce == -1;
-    unsigned m = __ballot_sync(FULL, want);
-    if (m != 0 && __ldcg(a.next_item) >= a.total_items) m = 0;  // dispenser already dry: no atomic (warp-uniform up to a race that only costs one)
-    if (m != 0) {
-        const int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(a.next_item, (unsigned long long)__popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        const unsigned long long item = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-        if (want && item < a.total_items) {
-            const unsigned long long per_tile = 32ull * (unsigned long long)a.spp_count;
-            const unsigned int tile = (unsigned int)(item / per_tile);
-            const unsigned int in_tile = (unsigned int)(item - (unsigned long long)tile * per_tile);
-            const int pi = (int)(in_tile & 31u);
+    {   // empty slots (just emptied or empty before) queue up for a new path sample
+        const bool want = bounce == -1;
+        const unsigned m = __ballot_sync(FULL, want);
+        int wbase = 0;
+        if (lane == 0 && m != 0) wbase = atomicAdd(&s_count, __popc(m));
+        wbase = __shfl_sync(FULL, wbase, 0);
+        if (want) s_queue[wbase + __popc(m & ((1u << lane) - 1u))] = tid;
+    }
+    __syncthreads();
+
+    // ---- pass 2: new camera rays, densely ----
+    const int q = s_count;
+    if (q > 0) {
+        if (tid == 0) s_base = __ldcg(a.next_item) < a.total_items ? atomicAdd(a.next_item, (unsigned long long)q) : a.total_items;
+        __syncthreads();
+        const unsigned long long item = s_base + (unsigned long long)tid;
+        if (tid < q && item < a.total_items) {
+            // item -> (tile, sample, pixel of the tile)
+            const unsigned long long group = item >> 5;  // one (tile, sample) pair
+            const unsigned int tile = (unsigned int)(group / (unsigned long long)a.spp_count);
+            const unsigned int smp_i = (unsigned int)(group - (unsigned long long)tile * (unsigned long long)a.spp_count);
+            const int pi = (int)(item & 31ull);
             const int px = (int)(tile % (unsigned int)a.tiles_x) * kTileW + (pi & (kTileW - 1));
             const int row = (int)(tile / (unsigned int)a.tiles_x) * kTileH + (pi / kTileW);  // row 0 = top
             if (px < a.width && row < a.height) {  // (a pixel beyond a ragged image edge: the slot retries next iteration)
-                smp.pixel = (uint32_t)(row * a.width + px);
-                smp.sample = (uint32_t)a.spp_begin + (in_tile >> 5);
-                smp.bounce = 0;
-                camera_ray(a.cam, a.width, a.height, px, a.height - 1 - row, smp, ray);
-                pc = PathColor{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
-                bounce = 0;
-                fresh = true;
+                Sampler s2{a.k0, a.k1, (uint32_t)(row * a.width + px), (uint32_t)a.spp_begin + smp_i, 0u};
+                RayD r2;
+                camera_ray(a.cam, a.width, a.height, px, a.height - 1 - row, s2, r2);
+                const int owner = s_queue[tid];
+                s_ray[0][owner] = r2.o.x; s_ray[1][owner] = r2.o.y; s_ray[2][owner] = r2.o.z;
+                s_ray[3][owner] = r2.d.x; s_ray[4][owner] = r2.d.y; s_ray[5][owner] = r2.d.z;
+                s_ray[6][owner] = r2.time;
+                s_pix[0][owner] = s2.pixel; s_pix[1][owner] = s2.sample;
+                s_staged[owner] = 1;
             }
         }
+        __syncthreads();
+        if (s_staged[tid]) {
+            ray.o = mk(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]);
+            ray.d = mk(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
+            ray.time = s_ray[6][tid];
+            smp.pixel = s_pix[0][tid];
+            smp.sample = s_pix[1][tid];
+            pc = PathColor{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+            bounce = 0;
+            fresh = true;
+        }
     }
+
+    // ---- pass 3: the new ray: media first (their scatter point bounds the surface search), then out to the pool ----
     if (fresh) {
-        // ---- the new ray: media first (their scatter point bounds the surface search), then out to the pool ----
         smp.bounce = (uint32_t)bounce;
         Best best{1.7976931348623157e308, -1, 0};
         if (a.sc.n_media > 0) {
@@ -1119,8 +1179,6 @@ __global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArg
         a.pool.rad_r[i] = pc.rad_r; a.pool.rad_g[i] = pc.rad_g; a.pool.rad_b[i] = pc.rad_b;
         a.pool.pixel[i] = smp.pixel; a.pool.sample[i] = smp.sample;
         a.pool.bounce[i] = bounce;
-    } else if (dirty) {
-        a.pool.bounce[i] = -1;
     }
     if (active_out) {
         const unsigned am = __ballot_sync(FULL, fresh);
