@@ -344,20 +344,31 @@ def run_ours(args):
     # ---- end to end through the public API, host buffers ----
     h2d = [0]
 
+    e2e_log = []
+
     def step_e2e():
+        t0 = time.perf_counter()
         sc = R.DeviceScene(ctx, desc)  # flatten + BVH build on the host, H2D of the whole scene
+        t1 = time.perf_counter()
         h2d[0] = sc.info()["device_bytes"] + sum(desc.desc.images[i].width * desc.desc.images[i].height * 4
                                                   for i in range(desc.desc.n_images) if desc.desc.images[i].rgba)
         render_step(sc)
+        t2 = time.perf_counter()
         if rank == 0:
             rgba_host.copy_(d_rgba, non_blocking=True)  # D2H of the frame
         torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter()
         sc.close()
+        t4 = time.perf_counter()
+        e2e_log.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
     for _ in range(2):
         step_e2e()
     e2e_steps = max(2, min(args.steps, 4))
     e2e_ms, _ = timed(step_e2e, e2e_steps)
     e2e_value = n_px * args.spp * world * e2e_steps / (e2e_ms * 1e-3)
+    if rank == 0:
+        sys.stderr.write("e2e host phases per step (scene create, render call, sync + D2H, scene destroy) ms: " +
+                         "; ".join("/".join(f"{1e3 * x:.1f}" for x in row) for row in e2e_log) + "\n")
 
     # ---- roofline bookkeeping (rank 0, outside the timed region): counting build of the kernel ----
     line = None

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -31,6 +32,27 @@ int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t e__ = (call);                     \
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
+
+// Device allocations of destroyed scenes, kept for the next rtx_scene_create on the same device: a
+// caller that re-uploads its scene every frame then pays two memcpys instead of cudaMalloc /
+// cudaMallocArray / cudaCreateTextureObject / cudaFree (the frees stall sporadically for 0.1-1 s).
+struct ArenaSlot {
+    void* p;
+    size_t bytes;
+};
+struct ArraySlot {
+    cudaArray_t arr;
+    cudaTextureObject_t tex;
+    int w, h;
+};
+struct DeviceCache {
+    std::mutex m;
+    std::vector<ArenaSlot> arenas;
+    std::vector<ArraySlot> arrays;
+};
+constexpr int kMaxDevices = 64;
+constexpr size_t kCacheKeep = 4;
+DeviceCache g_cache[kMaxDevices];
 
 }  // namespace
 
@@ -68,9 +90,8 @@ struct rtx_scene {
     rtx::SceneView view{};
     rtx::CameraView camera{};
     void* d_arena = nullptr;
-    size_t arena_bytes = 0;
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> textures;
+    size_t arena_bytes = 0, arena_capacity = 0;
+    std::vector<ArraySlot> images;
     int32_t n_nodes = 0, n_records = 0, n_xforms = 0;
 };
 
@@ -195,28 +216,40 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
         rtx::DImage& di = dimages[(size_t)i];
         di.tex = 0; di.width = im.width; di.height = im.height;
         if (!im.rgba || im.width <= 0 || im.height <= 0) continue;
-        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-        cudaArray_t arr = nullptr;
-        cudaError_t e = cudaMallocArray(&arr, &fmt, (size_t)im.width, (size_t)im.height);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocArray"));
-        s->arrays.push_back(arr);
-        e = cudaMemcpy2DToArrayAsync(arr, 0, 0, im.rgba, (size_t)im.width * 4, (size_t)im.width * 4, (size_t)im.height,
+        ArraySlot slot{nullptr, 0, im.width, im.height};
+        if (c->device < kMaxDevices) {  // an array + texture object of the same size left by a destroyed scene
+            DeviceCache& dc = g_cache[c->device];
+            std::lock_guard<std::mutex> lock(dc.m);
+            for (size_t k = 0; k < dc.arrays.size(); ++k)
+                if (dc.arrays[k].w == im.width && dc.arrays[k].h == im.height) {
+                    slot = dc.arrays[k];
+                    dc.arrays.erase(dc.arrays.begin() + (long)k);
+                    break;
+                }
+        }
+        cudaError_t e = cudaSuccess;
+        if (!slot.arr) {
+            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+            e = cudaMallocArray(&slot.arr, &fmt, (size_t)im.width, (size_t)im.height);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocArray"));
+            cudaResourceDesc rd;
+            std::memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = slot.arr;
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;  // nearest texel, no filtering, no sRGB decode (Q23)
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            e = cudaCreateTextureObject(&slot.tex, &rd, &td, nullptr);
+            if (e != cudaSuccess) { cudaFreeArray(slot.arr); return bail(cuda_fail(e, "cudaCreateTextureObject")); }
+        }
+        s->images.push_back(slot);
+        e = cudaMemcpy2DToArrayAsync(slot.arr, 0, 0, im.rgba, (size_t)im.width * 4, (size_t)im.width * 4, (size_t)im.height,
                                      cudaMemcpyHostToDevice, c->stream);
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy2DToArray"));
-        cudaResourceDesc rd;
-        std::memset(&rd, 0, sizeof(rd));
-        rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = arr;
-        cudaTextureDesc td;
-        std::memset(&td, 0, sizeof(td));
-        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-        td.filterMode = cudaFilterModePoint;  // nearest texel, no filtering, no sRGB decode (Q23)
-        td.readMode = cudaReadModeElementType;
-        td.normalizedCoords = 0;
-        cudaTextureObject_t tex = 0;
-        e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaCreateTextureObject"));
-        s->textures.push_back(tex);
+        cudaTextureObject_t tex = slot.tex;
         di.tex = (unsigned long long)tex;
     }
 
@@ -243,8 +276,24 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     put(off_perlins, fs.perlins.data(), fs.perlins.size() * sizeof(rtx::DPerlin));
     put(off_images, dimages.data(), dimages.size() * sizeof(rtx::DImage));
     put(off_media, fs.media.data(), fs.media.size() * sizeof(rtx::DMedium));
-    cudaError_t e = cudaMalloc(&s->d_arena, total);
-    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scene)"));
+    if (c->device < kMaxDevices) {  // smallest cached arena that is large enough
+        DeviceCache& dc = g_cache[c->device];
+        std::lock_guard<std::mutex> lock(dc.m);
+        size_t pick = dc.arenas.size();
+        for (size_t k = 0; k < dc.arenas.size(); ++k)
+            if (dc.arenas[k].bytes >= total && (pick == dc.arenas.size() || dc.arenas[k].bytes < dc.arenas[pick].bytes)) pick = k;
+        if (pick < dc.arenas.size()) {
+            s->d_arena = dc.arenas[pick].p;
+            s->arena_capacity = dc.arenas[pick].bytes;
+            dc.arenas.erase(dc.arenas.begin() + (long)pick);
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (!s->d_arena) {
+        e = cudaMalloc(&s->d_arena, total);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scene)"));
+        s->arena_capacity = total;
+    }
     s->arena_bytes = total;
     e = cudaMemcpyAsync(s->d_arena, host.data(), total, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // `host` dies with this frame
@@ -273,9 +322,23 @@ int rtx_scene_destroy(rtx_scene* s) {
     if (!s) return RTX_OK;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();  // kernels still reading the arena (any stream)
-    for (auto t : s->textures) cudaDestroyTextureObject(t);
-    for (auto a : s->arrays) cudaFreeArray(a);
-    if (s->d_arena) cudaFree(s->d_arena);
+    DeviceCache* dc = s->device < kMaxDevices ? &g_cache[s->device] : nullptr;
+    for (auto& im : s->images) {
+        bool kept = false;
+        if (dc) {
+            std::lock_guard<std::mutex> lock(dc->m);
+            if (dc->arrays.size() < kCacheKeep) { dc->arrays.push_back(im); kept = true; }
+        }
+        if (!kept) { cudaDestroyTextureObject(im.tex); cudaFreeArray(im.arr); }
+    }
+    if (s->d_arena) {
+        bool kept = false;
+        if (dc) {
+            std::lock_guard<std::mutex> lock(dc->m);
+            if (dc->arenas.size() < kCacheKeep) { dc->arenas.push_back(ArenaSlot{s->d_arena, s->arena_capacity}); kept = true; }
+        }
+        if (!kept) cudaFree(s->d_arena);
+    }
     delete s;
     return RTX_OK;
 }
