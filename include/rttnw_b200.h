@@ -231,9 +231,9 @@ int rtx_ctx_sync(rtx_ctx* ctx);
 void* rtx_ctx_stream(rtx_ctx* ctx);
 /* number of CUDA kernels this context has launched so far (bookkeeping for benchmarks) */
 int rtx_ctx_kernel_launches(rtx_ctx* ctx, unsigned long long* out);
-/* Per-kernel timing of rtx_render (benchmark bookkeeping): when on, every shade / trace launch is
- * bracketed by CUDA events on the ctx stream and rtx_render waits for the last one before it
- * returns. rtx_ctx_profile_read returns the accumulated device milliseconds of the two kernels and
+/* Per-kernel timing of rtx_render (benchmark bookkeeping): when on, the shade / trace launches of
+ * every 8th iteration are bracketed by CUDA events on the ctx stream (scaled back up by 8) and
+ * rtx_render waits for the last one before it returns. rtx_ctx_profile_read returns the accumulated device milliseconds of the two kernels and
  * the number of (shade, trace) iterations they cover; reset != 0 clears the accumulators. */
 int rtx_ctx_set_profiling(rtx_ctx* ctx, int on);
 int rtx_ctx_profile_read(rtx_ctx* ctx, double* shade_ms, double* trace_ms,

@@ -484,8 +484,13 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     unsigned tgrid = (unsigned)c->trace_grid;
     if ((int64_t)tgrid * (rtx::kWfBlock / 32) * 32 > slots) tgrid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
     size_t prof_used = 0;
+    // every kProfStride-th iteration is bracketed (events between back-to-back launches cost ~10 % when every
+    // launch has them); the accumulated times are scaled back up by the stride
+    constexpr int kProfStride = 8;
+    long long iteration = 0;
+    bool prof_now = false;
     auto prof_mark = [&](void) -> cudaError_t {
-        if (!c->profiling) return cudaSuccess;
+        if (!prof_now) return cudaSuccess;
         if (prof_used == c->prof_events.size()) {
             cudaEvent_t e;
             cudaError_t err = cudaEventCreate(&e);
@@ -503,6 +508,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 active = c->d_active + par;
                 CU(cudaMemsetAsync(active, 0, sizeof(unsigned int), c->stream));
             }
+            prof_now = c->profiling && (iteration++ % kProfStride) == 0;
             CU(prof_mark());
             if (counted) {
                 rtx::wf_shade_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
@@ -549,10 +555,10 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
         for (size_t q = 0; q + 3 < prof_used; q += 4) {
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, c->prof_events[q], c->prof_events[q + 1]));
-            c->prof_shade_ms += ms;
+            c->prof_shade_ms += ms * kProfStride;
             CU(cudaEventElapsedTime(&ms, c->prof_events[q + 2], c->prof_events[q + 3]));
-            c->prof_trace_ms += ms;
-            c->prof_iterations += 1;
+            c->prof_trace_ms += ms * kProfStride;
+            c->prof_iterations += kProfStride;
         }
     }
     return RTX_OK;

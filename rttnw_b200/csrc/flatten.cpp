@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -64,9 +65,11 @@ struct BvhBuilder {
     std::vector<Record>& records;
     std::vector<Item>& items;
     static constexpr int kBins = 16;
-    static constexpr int kMaxLeaf = 4;
+    static constexpr int kMaxLeafLimit = 4;
     static constexpr double kCostTraverse = 1.0;  // one 64-byte node fetch + two fp32 slab tests
-    static constexpr double kCostPrim = 2.0;      // one 96-byte record + an f64 intersection
+    // tunables (RTX_BVH_LEAF, RTX_BVH_CPRIM override for experiments)
+    int kMaxLeaf = 4;
+    double kCostPrim = 2.0;  // one 96-byte record + an f64 intersection, in units of kCostTraverse
 
     struct Tmp {
         Aabb box;
@@ -82,7 +85,10 @@ struct BvhBuilder {
     };
     std::vector<Prim> prims;
 
-    BvhBuilder(std::vector<BvhNode>& n, std::vector<Record>& r, std::vector<Item>& it) : nodes(n), records(r), items(it) {}
+    BvhBuilder(std::vector<BvhNode>& n, std::vector<Record>& r, std::vector<Item>& it) : nodes(n), records(r), items(it) {
+        if (const char* v = std::getenv("RTX_BVH_LEAF")) kMaxLeaf = std::min(kMaxLeafLimit, std::max(1, std::atoi(v)));
+        if (const char* v = std::getenv("RTX_BVH_CPRIM")) kCostPrim = std::max(0.1, std::atof(v));
+    }
 
     int build_range(int lo, int hi) {
         Tmp t;
@@ -752,7 +758,7 @@ struct Checker {
             } else {
                 int32_t v = ~ref;
                 int first = v >> 4, count = v & 15;
-                if (count > BvhBuilder::kMaxLeaf && count != 0) return fail("leaf larger than the maximum");
+                if (count > BvhBuilder::kMaxLeafLimit && count != 0) return fail("leaf larger than the maximum");
                 if (first < 0 || first + count > (int)fs.records.size()) return fail("leaf range out of bounds");
                 for (int i = 0; i < count; ++i) {
                     const Record& r = fs.records[(size_t)(first + i)];

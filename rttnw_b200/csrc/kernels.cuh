@@ -607,10 +607,10 @@ __device__ __forceinline__ float perlin_turbulence(const DPerlin* tab, float px,
     return acc;
 }
 
-// Texture::value. (u, v) are only meaningful when the texture's uses-uv flag is set.
-__device__ __forceinline__ f3 texture_value(const SceneView& sc, int32_t ti, float u, float v, d3 p) {
+// CheckerTexture (texture.rs:15-30, Q21) selects a child; children may nest. Returns the texture that
+// finally gets evaluated.
+__device__ __forceinline__ DTexture resolve_texture(const SceneView& sc, int32_t ti, d3 p) {
     DTexture t = sc.textures[ti];
-    // CheckerTexture (texture.rs:15-30, Q21) selects a child; children may nest
 #pragma unroll 1
     for (int guard = 0; guard < 8 && t.kind == RTX_TEX_CHECKER; ++guard) {
         // f64 products keep the stripe edges of the radius-1000 ground sphere where the reference puts them;
@@ -620,10 +620,18 @@ __device__ __forceinline__ f3 texture_value(const SceneView& sc, int32_t ti, flo
         for (int c = 0; c < 3; ++c) sines *= sinf((float)(10.0 * comp(p, c)));
         t = sc.textures[sines < 0.f ? t.a : t.b];
     }
+    return t;
+}
+// NoiseTexture::value, texture.rs:52-59 (Q22): grey 0.5 (1 + sin(scale z + 10 turb(p)))
+__device__ __forceinline__ float noise_value(const SceneView& sc, int32_t perlin, float scale, float px, float py, float pz) {
+    float turb = perlin_turbulence(sc.perlins + perlin, px, py, pz);
+    return 0.5f * (1.f + sinf(scale * pz + 10.f * turb));
+}
+// Texture::value of a resolved texture. (u, v) are only meaningful when the texture's uses-uv flag is set.
+__device__ __forceinline__ f3 texture_eval(const SceneView& sc, const DTexture& t, float u, float v, d3 p) {
     if (t.kind == RTX_TEX_SOLID) return mkf(t.f[0], t.f[1], t.f[2]);
-    if (t.kind == RTX_TEX_NOISE) {  // texture.rs:52-59 (Q22)
-        float turb = perlin_turbulence(sc.perlins + t.a, (float)p.x, (float)p.y, (float)p.z);
-        float g = 0.5f * (1.f + sinf(t.f[0] * (float)p.z + 10.f * turb));
+    if (t.kind == RTX_TEX_NOISE) {
+        float g = noise_value(sc, t.a, t.f[0], (float)p.x, (float)p.y, (float)p.z);
         return mkf(g, g, g);
     }
     if (t.kind == RTX_TEX_IMAGE) {  // texture.rs:77-106 (Q23): nearest texel, bytes / 255
@@ -662,9 +670,32 @@ struct PathColor {
     float rad_r, rad_g, rad_b;  // radiance gathered so far
 };
 
+// What shade_hit leaves for the caller to apply: the texture value multiplies the throughput (scatter) or
+// is added as emitted radiance. With kDeferNoise a Perlin texture is NOT evaluated here: `noise_perlin`
+// >= 0 names the table and the caller evaluates noise_value(noise_perlin, noise_scale, p) — densely, for all
+// the threads of the CTA that need it, instead of 7 octaves x 8 lattice corners on a mostly idle warp.
+struct Albedo {
+    float r, g, b;
+    bool emissive;
+    int32_t noise_perlin;
+    float noise_scale, px, py, pz;
+};
+__device__ __forceinline__ void apply_albedo(PathColor& pc, const Albedo& al) {
+    if (al.emissive) {
+        pc.rad_r += pc.thr_r * al.r; pc.rad_g += pc.thr_g * al.g; pc.rad_b += pc.thr_b * al.b;
+    } else {
+        pc.thr_r *= al.r; pc.thr_g *= al.g; pc.thr_b *= al.b;
+    }
+}
+
+template <bool kDeferNoise>
 __device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __restrict__ background, int32_t max_depth, RayD& ray,
-                                          const Best& best, const Sampler& smp, PathColor& pc, int& bounce) {
+                                          const Best& best, const Sampler& smp, PathColor& pc, int& bounce, Albedo& al) {
     bool end_path = false;
+    al.r = al.g = al.b = 1.f;
+    al.emissive = false;
+    al.noise_perlin = -1;
+    al.noise_scale = al.px = al.py = al.pz = 0.f;
     if (best.rec < 0) {  // background (Q8)
         pc.rad_r += pc.thr_r * background[0]; pc.rad_g += pc.thr_g * background[1]; pc.rad_b += pc.thr_b * background[2];
         end_path = true;
@@ -689,11 +720,18 @@ __device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __re
                 tv = acosf(-(float)ho.on.y) / PI;
                 tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
             }
-            f3 tex = texture_value(sc, mtex, tu, tv, ho.p);
-            alb_r = tex.x; alb_g = tex.y; alb_b = tex.z;
+            DTexture t = resolve_texture(sc, mtex, ho.p);
+            if (kDeferNoise && t.kind == RTX_TEX_NOISE) {
+                al.noise_perlin = t.a;
+                al.noise_scale = t.f[0];
+                al.px = (float)ho.p.x; al.py = (float)ho.p.y; al.pz = (float)ho.p.z;
+            } else {
+                f3 tex = texture_eval(sc, t, tu, tv, ho.p);
+                alb_r = tex.x; alb_g = tex.y; alb_b = tex.z;
+            }
         }
         if (mkind == RTX_MAT_DIFFUSE_LIGHT) {  // material.rs:242-250 (Q24): emits on both sides, never scatters
-            pc.rad_r += pc.thr_r * alb_r; pc.rad_g += pc.thr_g * alb_g; pc.rad_b += pc.thr_b * alb_b;
+            al.emissive = true;
             end_path = true;
         } else {
             // The random draws of scatter(): block (SCATTER, 0) serves every material — words 0..2 are the
@@ -744,12 +782,12 @@ __device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __re
                     alb_r = alb_g = alb_b = 1.f;
                 }
             }
-            pc.thr_r *= alb_r; pc.thr_g *= alb_g; pc.thr_b *= alb_b;
             ray.d = nd;
             ray.o = ho.p;
             ++bounce;
             if (bounce >= max_depth) end_path = true;  // color(depth = 0) returns 0
         }
+        al.r = alb_r; al.g = alb_g; al.b = alb_b;  // (a deferred noise value overwrites this grey)
     }
     return end_path;
 }
@@ -930,7 +968,9 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
             // ================= shade phase =================
             bool fresh = false;  // this lane leaves the phase with a new ray to trace
             if (st == ST_SHADE) {
-                const bool end_path = shade_hit(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce);
+                Albedo al;
+                const bool end_path = shade_hit<false>(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce, al);
+                apply_albedo(pc, al);
                 if (end_path) {
                     // one path sample done: add it to its pixel (sum r, g, b, count)
                     atomicAdd(accum + smp.pixel, make_float4(pc.rad_r, pc.rad_g, pc.rad_b, 1.0f));
@@ -1095,7 +1135,9 @@ __global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArg
     RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
     PathColor pc{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
     Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
-    bool fresh = false;
+    bool fresh = false, shaded = false, ended = false;
+    Albedo al;
+    al.noise_perlin = -1;
     if (bounce >= 0) {
         ray.o = mk(a.pool.ox[i], a.pool.oy[i], a.pool.oz[i]);
         ray.d = mk(a.pool.dx[i], a.pool.dy[i], a.pool.dz[i]);
@@ -1105,7 +1147,14 @@ __global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArg
         smp.pixel = a.pool.pixel[i];
         smp.sample = a.pool.sample[i];
         smp.bounce = (uint32_t)bounce;
-        if (shade_hit(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce)) {
+        // (a dense shared-memory pass for Perlin textures — shade_hit<true> + noise_value for queued threads — was
+        // measured: neutral on scenes 3 / 5, -2 % on scene 9 for its two extra barriers; not used)
+        ended = shade_hit<false>(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce, al);
+        shaded = true;
+    }
+    if (shaded) {
+        apply_albedo(pc, al);
+        if (ended) {
             atomicAdd(accum + smp.pixel, make_float4(pc.rad_r, pc.rad_g, pc.rad_b, 1.0f));  // one path sample done
             bounce = -1;
             a.pool.bounce[i] = -1;
