@@ -73,15 +73,12 @@ struct rtx_ctx {
     unsigned long long* h_status = nullptr;      // pinned: [2][2] = {active, next_item} per batch parity
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
     int wf_batch = 8;
-    int wf_trace = 0;  // 0: one slot per thread (default), 1: persistent vote-batched (RTX_WF_TRACE=vote), 2: persistent refill (=refill)
     unsigned long long launches = 0;  // kernels launched by this context (rtx_ctx_kernel_launches)
     // optional per-kernel timing of the wavefront driver (rtx_ctx_set_profiling): CUDA events around every launch
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // grows on demand; [4 * iteration + {0,1,2,3}] = shade begin/end, trace begin/end
     double prof_shade_ms = 0, prof_trace_ms = 0;
     unsigned long long prof_iterations = 0;
-    unsigned int* d_next_slot = nullptr;  // [wf_batch] per-iteration slot counters of the persistent trace kernel
-    int trace_grid = 0;
     int w_node = 1, w_leaf = 1, w_shade = 1;  // render_kernel phase weights (RTX_W_NODE / RTX_W_LEAF / RTX_W_SHADE override)
 };
 
@@ -143,7 +140,6 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->pool_slots_wanted = env_int("RTX_WF_SLOTS", c->pool_slots_wanted);
     c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
-    if (const char* m = std::getenv("RTX_WF_TRACE")) c->wf_trace = std::strcmp(m, "vote") == 0 ? 1 : (std::strcmp(m, "refill") == 0 ? 2 : 0);
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -160,7 +156,6 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     cudaFree(c->d_pool);
     cudaFree(c->d_next_item);
     cudaFree(c->d_active);
-    cudaFree(c->d_next_slot);
     if (c->h_status) cudaFreeHost(c->h_status);
     for (auto& e : c->batch_done)
         if (e) cudaEventDestroy(e);
@@ -424,12 +419,7 @@ static int wf_prepare(rtx_ctx* c, int64_t slots) {
     }
     if (!c->d_next_item) CU(cudaMalloc(&c->d_next_item, sizeof(unsigned long long)));
     if (!c->d_active) CU(cudaMalloc(&c->d_active, 2 * sizeof(unsigned int)));
-    if (!c->d_next_slot) {
-        CU(cudaMalloc(&c->d_next_slot, (size_t)c->wf_batch * sizeof(unsigned int)));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtx::wf_trace_persistent_kernel<false>, rtx::kWfBlock, 0));
-        c->trace_grid = c->sm_count * (per_sm < 1 ? 1 : per_sm);
-    }
+
     if (!c->h_status) CU(cudaMallocHost(&c->h_status, 4 * sizeof(unsigned long long)));
     for (auto& e : c->batch_done)
         if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -480,9 +470,6 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     float4* acc = reinterpret_cast<float4*>(d_accum);
     const unsigned grid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
     const int batch = c->wf_batch;
-    rtx::TraceTune tune{c->w_node, c->w_leaf, c->w_shade, c->node_burst, std::getenv("RTX_SPECULATE") ? 1 : 0};
-    unsigned tgrid = (unsigned)c->trace_grid;
-    if ((int64_t)tgrid * (rtx::kWfBlock / 32) * 32 > slots) tgrid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
     size_t prof_used = 0;
     // every kProfStride-th iteration is bracketed (events between back-to-back launches cost ~10 % when every
     // launch has them); the accumulated times are scaled back up by the stride
@@ -501,7 +488,6 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     };
     for (int k = 0;; ++k) {
         const int par = k & 1;
-        if (c->wf_trace) CU(cudaMemsetAsync(c->d_next_slot, 0, (size_t)batch * sizeof(unsigned int), c->stream));
         for (int it = 0; it < batch; ++it) {
             unsigned int* active = nullptr;
             if (it == batch - 1) {
@@ -514,24 +500,12 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 rtx::wf_shade_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
                 CU(prof_mark());
                 CU(prof_mark());
-                if (c->wf_trace == 2)
-                    rtx::wf_trace_refill_kernel<true><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, d_ray_count, c->d_counters);
-                else if (c->wf_trace)
-                    rtx::wf_trace_persistent_kernel<true><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, tune,
-                                                                                                 d_ray_count, c->d_counters);
-                else
-                    rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
+                rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
             } else {
                 rtx::wf_shade_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, nullptr);
                 CU(prof_mark());
                 CU(prof_mark());
-                if (c->wf_trace == 2)
-                    rtx::wf_trace_refill_kernel<false><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, d_ray_count, nullptr);
-                else if (c->wf_trace)
-                    rtx::wf_trace_persistent_kernel<false><<<tgrid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, c->d_next_slot + it, tune,
-                                                                                                  d_ray_count, nullptr);
-                else
-                    rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);
+                rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);
             }
             CU(prof_mark());
         }

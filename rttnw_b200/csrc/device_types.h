@@ -26,7 +26,9 @@ enum RecType : int32_t {
     REC_RECT_XY = 2,   // d = {a0, a1, b0, b1, k}  (axis0, axis1, k_axis) = (0,1,2)
     REC_RECT_XZ = 3,   //                                                   (0,2,1)
     REC_RECT_YZ = 4,   //                                                   (1,2,0)
-    REC_INSTANCE = 5,  // a = BVH root of the instanced group, c = chain index (SceneView::chains)
+    REC_INSTANCE = 5,  // (unused: wrapped primitives carry their chain, see Record::c)
+    REC_BOX = 7,       // Cube: d = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}; a = index of the first of its six rectangle
+                       // records (Cube::new order), b = first primitive id
     REC_MEDIUM = 6     // a = phase texture, b = prim id, c = boundary BVH root, or -1: the boundary is the
                        // untransformed sphere d[4..7] = {cx, cy, cz, r}, or <= -2: it is the box
                        // d[4..9] = {lo, hi} in the space of chain (-2 - c);
@@ -41,7 +43,7 @@ struct alignas(16) Record {
     int32_t type;
     int32_t a;  // geometry: material index
     int32_t b;  // geometry: primitive id
-    int32_t c;
+    int32_t c;  // geometry: wrapper chain index (SceneView::chains; 0 = none, the primitive is in world space)
     double d[10];
 };
 static_assert(sizeof(Record) == 96, "Record must be 96 bytes");

@@ -4,12 +4,13 @@
 // item (:153-163), wrappers Translate/YRotate re-express the ray (:599-605, :686-697) and
 // BvhTree::hit recurses through Arc<dyn Hittable> (:355-368). Here the same tree is turned,
 // once, into:
-//   * leaf records (sphere / moving sphere / rectangle; a Cube becomes its six rectangles
-//     in the order of Cube::new, :560-569),
+//   * leaf records (sphere / moving sphere / rectangle / box; a Cube is one box item for the
+//     traversal plus its six rectangles, in the order of Cube::new :560-569, for the hit record),
 //   * one transform chain per distinct wrapper path (outermost op first),
-//   * a BVH per instanced group, one over the world (identity-chain primitives and instance
-//     records) and one per ConstantMedium boundary; the media themselves are a short list
-//     with world bounds that every ray checks before it traverses (device_types.h, DMedium).
+//   * ONE BVH over the world, in world space (a wrapped primitive carries the index of its chain
+//     and world bounds; its f64 test pushes the ray through the chain), and one per general
+//     ConstantMedium boundary; the media themselves are a short list with world bounds that
+//     every ray checks before it traverses (device_types.h, DMedium).
 // Bounds are geometrically correct rotated bounds — NOT YRotate::new's (:654-672),
 // which the reference never uses for culling either.
 #include "flatten.hpp"
@@ -43,7 +44,7 @@ namespace {
 struct Item {
     Record rec;
     Aabb box;
-    bool solo() const { return rec.type == REC_INSTANCE; }  // must sit alone in its leaf
+    bool solo() const { return false; }  // (no record kind needs a leaf of its own any more)
 };
 
 float round_down(double v) {
@@ -259,25 +260,14 @@ struct BvhBuilder {
 // ---------------------------------------------------------------------------
 // Tree walk
 // ---------------------------------------------------------------------------
-struct Group {
-    std::vector<XformOp> chain;
-    std::vector<Item> items;
-};
+// One closest-hit query space: the world, or the boundary of a ConstantMedium. Every primitive in
+// it carries the index of its wrapper chain and WORLD-space bounds, so one BVH serves the whole
+// space and the traversal never switches coordinate systems (the f64 test of a wrapped primitive
+// pushes the ray through the chain first).
 struct World {
     bool is_boundary = false;
-    std::vector<std::vector<int>> paths;  // insertion order; paths[0] is the identity path if present
-    std::map<std::vector<int>, Group> groups;
+    std::vector<Item> items;
     std::vector<Item> media;
-    Group& group(const std::vector<int>& path, const std::vector<XformOp>& chain) {
-        auto it = groups.find(path);
-        if (it == groups.end()) {
-            paths.push_back(path);
-            Group g;
-            g.chain = chain;
-            it = groups.emplace(path, std::move(g)).first;
-        }
-        return it->second;
-    }
 };
 
 struct Flattener {
@@ -286,6 +276,7 @@ struct Flattener {
     std::string& err;
     std::vector<int> first_id;   // per node: first primitive id handed out, -1 = not visited
     std::vector<int> medium_ord; // per MEDIUM node
+    std::map<std::vector<int>, int32_t> chain_of_path;  // wrapper path (node indices) -> chain index
     int next_prim = 0, next_medium = 0;
     double t_a = 0, t_b = 1;  // time interval moving-sphere bounds must cover
 
@@ -293,45 +284,93 @@ struct Flattener {
 
     bool fail(const std::string& m) { err = m; return false; }
 
-    static void box_of_sphere(const double c[3], double r, Aabb& b) {
-        for (int i = 0; i < 3; ++i) { b.lo[i] = c[i] - std::fabs(r); b.hi[i] = c[i] + std::fabs(r); }
+    // object -> world: undo the chain, innermost op first
+    static void to_world(const std::vector<XformOp>& chain, double p[3]) {
+        for (size_t i = chain.size(); i-- > 0;) {
+            const XformOp& op = chain[i];
+            if (op.kind == XF_TRANSLATE) {
+                p[0] += op.v[0]; p[1] += op.v[1]; p[2] += op.v[2];
+            } else {
+                double s = op.v[0], c = op.v[1];
+                double x = c * p[0] + s * p[2];
+                double z = -s * p[0] + c * p[2];
+                p[0] = x; p[2] = z;
+            }
+        }
+    }
+    // World bounds of an object-space box under `chain`: the geometrically correct rotated bounds, NOT
+    // YRotate::new's (hittable.rs:654-672, Q15), padded for the rounding of the rotation arithmetic.
+    static Aabb world_box(const Aabb& ob, const std::vector<XformOp>& chain) {
+        if (chain.empty()) return ob;
+        Aabb wb;
+        wb.reset();
+        for (int corner = 0; corner < 8; ++corner) {
+            double p[3] = {(corner & 1) ? ob.hi[0] : ob.lo[0], (corner & 2) ? ob.hi[1] : ob.lo[1], (corner & 4) ? ob.hi[2] : ob.lo[2]};
+            to_world(chain, p);
+            wb.grow_point(p);
+        }
+        for (int i = 0; i < 3; ++i) {
+            double pad = 1e-12 * std::fmax(1.0, std::fmax(std::fabs(wb.lo[i]), std::fabs(wb.hi[i])));
+            wb.lo[i] -= pad; wb.hi[i] += pad;
+        }
+        return wb;
+    }
+    static Aabb world_sphere_box(const double c[3], double r, const std::vector<XformOp>& chain) {
+        double w[3] = {c[0], c[1], c[2]};
+        to_world(chain, w);  // a sphere is rotation invariant: move the centre
+        Aabb b;
+        for (int i = 0; i < 3; ++i) {
+            double pad = chain.empty() ? 0.0 : 1e-12 * std::fmax(1.0, std::fabs(w[i]) + std::fabs(r));
+            b.lo[i] = w[i] - std::fabs(r) - pad; b.hi[i] = w[i] + std::fabs(r) + pad;
+        }
+        return b;
     }
 
-    Item make_rect(int plane, double a0, double a1, double b0, double b1, double k, int material, int prim_id) {
-        Item it;
-        std::memset(&it.rec, 0, sizeof(it.rec));
-        it.rec.type = REC_RECT_XY + plane;
-        it.rec.a = material;
-        it.rec.b = prim_id;
-        it.rec.d[0] = a0; it.rec.d[1] = a1; it.rec.d[2] = b0; it.rec.d[3] = b1; it.rec.d[4] = k;
+    // Registers a wrapper path: its ops (for the way out) and their composition (for the way in).
+    int32_t chain_index(const std::vector<int>& path, const std::vector<XformOp>& chain) {
+        if (chain.empty()) return 0;
+        auto it = chain_of_path.find(path);
+        if (it != chain_of_path.end()) return it->second;
+        DChain c;
+        std::memset(&c, 0, sizeof(c));
+        c.cs = 1.0;
+        c.begin = (int32_t)out.xforms.size();
+        c.len = (int32_t)chain.size();
+        for (const auto& op : chain) {  // outermost first, the order the wrappers see the ray
+            out.xforms.push_back(op);
+            if (op.kind == XF_TRANSLATE) {
+                c.tx -= op.v[0]; c.ty -= op.v[1]; c.tz -= op.v[2];
+            } else {
+                double s = op.v[0], k = op.v[1];
+                double cs = k * c.cs - s * c.sn, sn = s * c.cs + k * c.sn;
+                double tx = k * c.tx - s * c.tz, tz = s * c.tx + k * c.tz;
+                c.cs = cs; c.sn = sn; c.tx = tx; c.tz = tz;
+            }
+        }
+        out.chains.push_back(c);
+        int32_t idx = (int32_t)out.chains.size() - 1;
+        chain_of_path.emplace(path, idx);
+        return idx;
+    }
+
+    // Rectangle record in its own space + its object-space bounds (Rectangle::bounding_box pads k by 1e-4,
+    // hittable.rs:532-546; ranges may be given reversed)
+    static Record rect_record(int plane, double a0, double a1, double b0, double b1, double k, int material, int prim_id, int32_t chain, Aabb& ob) {
+        Record r;
+        std::memset(&r, 0, sizeof(r));
+        r.type = REC_RECT_XY + plane;
+        r.a = material;
+        r.b = prim_id;
+        r.c = chain;
+        r.d[0] = a0; r.d[1] = a1; r.d[2] = b0; r.d[3] = b1; r.d[4] = k;
         static const int ax0[3] = {0, 0, 1}, ax1[3] = {1, 2, 2}, axk[3] = {2, 1, 0};
-        // Rectangle::bounding_box pads k by 1e-4 (hittable.rs:532-546); ranges may be given reversed
-        it.box.lo[ax0[plane]] = std::fmin(a0, a1); it.box.hi[ax0[plane]] = std::fmax(a0, a1);
-        it.box.lo[ax1[plane]] = std::fmin(b0, b1); it.box.hi[ax1[plane]] = std::fmax(b0, b1);
-        it.box.lo[axk[plane]] = k - 0.0001; it.box.hi[axk[plane]] = k + 0.0001;
-        return it;
+        ob.lo[ax0[plane]] = std::fmin(a0, a1); ob.hi[ax0[plane]] = std::fmax(a0, a1);
+        ob.lo[ax1[plane]] = std::fmin(b0, b1); ob.hi[ax1[plane]] = std::fmax(b0, b1);
+        ob.lo[axk[plane]] = k - 0.0001; ob.hi[axk[plane]] = k + 0.0001;
+        return r;
     }
 
     bool check_material(int m) { return m >= 0 && m < d.n_materials; }
-
-    // Are these exactly the six rectangles Cube::new makes for one box with lo < hi on every axis?
-    static bool is_cube(const std::vector<Item>& items, double lo[3], double hi[3]) {
-        if (items.size() != 6) return false;
-        static const int planes[6] = {0, 0, 1, 1, 2, 2};
-        for (int i = 0; i < 6; ++i)
-            if (items[(size_t)i].rec.type != REC_RECT_XY + planes[i]) return false;
-        const double* r0 = items[0].rec.d;
-        lo[0] = r0[0]; hi[0] = r0[1]; lo[1] = r0[2]; hi[1] = r0[3]; lo[2] = r0[4]; hi[2] = items[1].rec.d[4];
-        for (int i = 0; i < 3; ++i)
-            if (!(lo[i] < hi[i])) return false;
-        const double want[6][5] = {{lo[0], hi[0], lo[1], hi[1], lo[2]}, {lo[0], hi[0], lo[1], hi[1], hi[2]},
-                                   {lo[0], hi[0], lo[2], hi[2], lo[1]}, {lo[0], hi[0], lo[2], hi[2], hi[1]},
-                                   {lo[1], hi[1], lo[2], hi[2], lo[0]}, {lo[1], hi[1], lo[2], hi[2], hi[0]}};
-        for (int i = 0; i < 6; ++i)
-            for (int k = 0; k < 5; ++k)
-                if (items[(size_t)i].rec.d[k] != want[i][k]) return false;
-        return true;
-    }
 
     bool collect(int ni, std::vector<int>& path, std::vector<XformOp>& chain, World& w, int depth) {
         if (ni < 0 || ni >= d.n_nodes) return fail("node index out of range");
@@ -345,9 +384,10 @@ struct Flattener {
                 Item it;
                 std::memset(&it.rec, 0, sizeof(it.rec));
                 it.rec.type = REC_SPHERE; it.rec.a = n.material; it.rec.b = first_id[(size_t)ni];
+                it.rec.c = chain_index(path, chain);
                 for (int i = 0; i < 4; ++i) it.rec.d[i] = f[i];
-                box_of_sphere(f, f[3], it.box);
-                w.group(path, chain).items.push_back(it);
+                it.box = world_sphere_box(f, f[3], chain);
+                w.items.push_back(it);
                 return true;
             }
             case RTX_NODE_MOVING_SPHERE: {
@@ -356,6 +396,7 @@ struct Flattener {
                 Item it;
                 std::memset(&it.rec, 0, sizeof(it.rec));
                 it.rec.type = REC_MSPHERE; it.rec.a = n.material; it.rec.b = first_id[(size_t)ni];
+                it.rec.c = chain_index(path, chain);
                 double r = f[6], t0 = f[7], t1 = f[8];
                 for (int i = 0; i < 3; ++i) { it.rec.d[i] = f[i]; it.rec.d[3 + i] = f[3 + i] - f[i]; }
                 it.rec.d[6] = r; it.rec.d[7] = t0; it.rec.d[8] = 1.0 / (t1 - t0);
@@ -365,11 +406,9 @@ struct Flattener {
                 for (double t : ts) {
                     double c[3];
                     for (int i = 0; i < 3; ++i) c[i] = f[i] + ((t - t0) / (t1 - t0)) * (f[3 + i] - f[i]);
-                    Aabb b;
-                    box_of_sphere(c, r, b);
-                    it.box.grow(b);
+                    it.box.grow(world_sphere_box(c, r, chain));
                 }
-                w.group(path, chain).items.push_back(it);
+                w.items.push_back(it);
                 return true;
             }
             case RTX_NODE_RECT_XY:
@@ -377,22 +416,51 @@ struct Flattener {
             case RTX_NODE_RECT_YZ: {
                 if (!check_material(n.material)) return fail("rectangle: bad material index");
                 if (first_id[(size_t)ni] < 0) first_id[(size_t)ni] = next_prim++;
-                w.group(path, chain).items.push_back(
-                    make_rect(n.kind - RTX_NODE_RECT_XY, f[0], f[1], f[2], f[3], f[4], n.material, first_id[(size_t)ni]));
+                Item it;
+                Aabb ob;
+                it.rec = rect_record(n.kind - RTX_NODE_RECT_XY, f[0], f[1], f[2], f[3], f[4], n.material, first_id[(size_t)ni],
+                                     chain_index(path, chain), ob);
+                it.box = world_box(ob, chain);
+                w.items.push_back(it);
                 return true;
             }
             case RTX_NODE_CUBE: {
                 if (!check_material(n.material)) return fail("cube: bad material index");
                 if (first_id[(size_t)ni] < 0) { first_id[(size_t)ni] = next_prim; next_prim += 6; }
                 int id = first_id[(size_t)ni];
-                Group& g = w.group(path, chain);
-                // Cube::new, hittable.rs:560-569 with Plane::points :451-479
-                g.items.push_back(make_rect(0, f[0], f[3], f[1], f[4], f[2], n.material, id + 0));
-                g.items.push_back(make_rect(0, f[0], f[3], f[1], f[4], f[5], n.material, id + 1));
-                g.items.push_back(make_rect(1, f[0], f[3], f[2], f[5], f[1], n.material, id + 2));
-                g.items.push_back(make_rect(1, f[0], f[3], f[2], f[5], f[4], n.material, id + 3));
-                g.items.push_back(make_rect(2, f[1], f[4], f[2], f[5], f[0], n.material, id + 4));
-                g.items.push_back(make_rect(2, f[1], f[4], f[2], f[5], f[3], n.material, id + 5));
+                int32_t ch = chain_index(path, chain);
+                // Cube::new, hittable.rs:560-569 with Plane::points :451-479: six rectangles, in this order
+                Aabb ob[6];
+                Record rr[6] = {rect_record(0, f[0], f[3], f[1], f[4], f[2], n.material, id + 0, ch, ob[0]),
+                                rect_record(0, f[0], f[3], f[1], f[4], f[5], n.material, id + 1, ch, ob[1]),
+                                rect_record(1, f[0], f[3], f[2], f[5], f[1], n.material, id + 2, ch, ob[2]),
+                                rect_record(1, f[0], f[3], f[2], f[5], f[4], n.material, id + 3, ch, ob[3]),
+                                rect_record(2, f[1], f[4], f[2], f[5], f[0], n.material, id + 4, ch, ob[4]),
+                                rect_record(2, f[1], f[4], f[2], f[5], f[3], n.material, id + 5, ch, ob[5])};
+                if (f[0] < f[3] && f[1] < f[4] && f[2] < f[5]) {
+                    // A proper box: ONE traversal item. A line meets the six rectangles exactly where it enters
+                    // and where it leaves the box, so the closest rectangle hit in [t_min, t_max] is the entry
+                    // face, or the exit face when the ray starts inside — one f64 slab computation (REC_BOX).
+                    // The six rectangle records stay (outside every leaf) for the hit record of the face.
+                    Item it;
+                    std::memset(&it.rec, 0, sizeof(it.rec));
+                    it.rec.type = REC_BOX;
+                    it.rec.a = (int32_t)out.records.size();
+                    it.rec.b = id;
+                    it.rec.c = ch;
+                    for (int k = 0; k < 6; ++k) { out.records.push_back(rr[k]); it.rec.d[k] = f[k]; }
+                    Aabb cb;
+                    for (int k = 0; k < 3; ++k) { cb.lo[k] = f[k] - 0.0001; cb.hi[k] = f[3 + k] + 0.0001; }
+                    it.box = world_box(cb, chain);
+                    w.items.push_back(it);
+                } else {  // degenerate or reversed extents: keep the reference's six rectangles as they are
+                    for (int k = 0; k < 6; ++k) {
+                        Item it;
+                        it.rec = rr[k];
+                        it.box = world_box(ob[k], chain);
+                        w.items.push_back(it);
+                    }
+                }
                 return true;
             }
             case RTX_NODE_LIST:
@@ -438,32 +506,21 @@ struct Flattener {
                 Aabb bounds;
                 Item it;
                 std::memset(&it.rec, 0, sizeof(it.rec));
-                // The common case (scenes.rs:282-301): the boundary is one untransformed Sphere. Its two
-                // boundary.hit() calls (hittable.rs:745-752) then reduce to the two roots of one quadratic.
-                const Group* only = (bw.paths.size() == 1 && bw.media.empty()) ? &bw.groups[bw.paths[0]] : nullptr;
+                const Item* only = bw.items.size() == 1 ? &bw.items[0] : nullptr;
                 int32_t root = -1;
-                double box_lo[3], box_hi[3];
-                if (only && only->chain.empty() && only->items.size() == 1 && only->items[0].rec.type == REC_SPHERE) {
-                    for (int i = 0; i < 4; ++i) it.rec.d[4 + i] = only->items[0].rec.d[i];
-                    bounds = only->items[0].box;
-                } else if (only && is_cube(only->items, box_lo, box_hi)) {
-                    // The other shipped case (scenes.rs:213-233): the boundary is one Cube, possibly under
-                    // Translate / YRotate wrappers. A line meets the six rectangles of a box exactly where it
-                    // enters and where it leaves, so the two boundary.hit() calls are one f64 slab computation
-                    // in the cube's own space: c = -2 - chain index.
-                    root = -2 - add_chain(only->chain);
-                    for (int i = 0; i < 3; ++i) { it.rec.d[4 + i] = box_lo[i]; it.rec.d[7 + i] = box_hi[i]; }
-                    bounds.reset();
-                    for (int corner = 0; corner < 8; ++corner) {
-                        double p[3] = {(corner & 1) ? box_hi[0] : box_lo[0], (corner & 2) ? box_hi[1] : box_lo[1],
-                                       (corner & 4) ? box_hi[2] : box_lo[2]};
-                        to_world(only->chain, p);
-                        bounds.grow_point(p);
-                    }
-                    for (int i = 0; i < 3; ++i) {
-                        double pad = 1e-4 + 1e-12 * std::fmax(1.0, std::fmax(std::fabs(bounds.lo[i]), std::fabs(bounds.hi[i])));
-                        bounds.lo[i] -= pad; bounds.hi[i] += pad;
-                    }
+                if (only && only->rec.type == REC_SPHERE && only->rec.c == 0) {
+                    // The common case (scenes.rs:282-301): the boundary is one untransformed Sphere. Its two
+                    // boundary.hit() calls (hittable.rs:745-752) then reduce to the two roots of one quadratic.
+                    for (int i = 0; i < 4; ++i) it.rec.d[4 + i] = only->rec.d[i];
+                    bounds = only->box;
+                } else if (only && only->rec.type == REC_BOX) {
+                    // The other shipped case (scenes.rs:213-233): one Cube, possibly under Translate / YRotate
+                    // wrappers — entry and exit of one f64 slab computation in the cube's own space.
+                    root = -2 - only->rec.c;
+                    for (int i = 0; i < 6; ++i) it.rec.d[4 + i] = only->rec.d[i];
+                    bounds = only->box;
+                    // the boundary's six face records are never looked at (a medium hit has its own record): drop them
+                    if ((size_t)only->rec.a + 6 == out.records.size()) out.records.resize((size_t)only->rec.a);
                 } else {
                     root = build_world(bw, bounds);
                 }
@@ -473,7 +530,7 @@ struct Flattener {
                 it.rec.c = root;
                 it.rec.d[0] = -1.0 / f[0];  // ConstantMedium::new, hittable.rs:731-735
                 it.rec.d[1] = (double)medium_ord[(size_t)ni];
-                it.rec.d[2] = (double)add_chain(chain);
+                it.rec.d[2] = (double)chain_index(path, chain);
                 it.box = bounds;
                 w.media.push_back(it);
                 return true;
@@ -483,83 +540,11 @@ struct Flattener {
         }
     }
 
-    // Registers a wrapper path: its ops (for the way out) and their composition (for the way in).
-    int32_t add_chain(const std::vector<XformOp>& chain) {
-        if (chain.empty()) return 0;
-        DChain c;
-        std::memset(&c, 0, sizeof(c));
-        c.cs = 1.0;
-        c.begin = (int32_t)out.xforms.size();
-        c.len = (int32_t)chain.size();
-        for (const auto& op : chain) {  // outermost first, the order the wrappers see the ray
-            out.xforms.push_back(op);
-            if (op.kind == XF_TRANSLATE) {
-                c.tx -= op.v[0]; c.ty -= op.v[1]; c.tz -= op.v[2];
-            } else {
-                double s = op.v[0], k = op.v[1];
-                double cs = k * c.cs - s * c.sn, sn = s * c.cs + k * c.sn;
-                double tx = k * c.tx - s * c.tz, tz = s * c.tx + k * c.tz;
-                c.cs = cs; c.sn = sn; c.tx = tx; c.tz = tz;
-            }
-        }
-        out.chains.push_back(c);
-        return (int32_t)out.chains.size() - 1;
-    }
-
-    // object -> world: undo the chain, innermost op first
-    static void to_world(const std::vector<XformOp>& chain, double p[3]) {
-        for (size_t i = chain.size(); i-- > 0;) {
-            const XformOp& op = chain[i];
-            if (op.kind == XF_TRANSLATE) {
-                p[0] += op.v[0]; p[1] += op.v[1]; p[2] += op.v[2];
-            } else {
-                double s = op.v[0], c = op.v[1];
-                double x = c * p[0] + s * p[2];
-                double z = -s * p[0] + c * p[2];
-                p[0] = x; p[2] = z;
-            }
-        }
-    }
-
-    // Stack entries a traversal of this world can need: the sentinel, one deferred sibling per level of
-    // the top BVH, the two entries an instance pushes, one per level of the deepest instanced BVH.
+    // Stack entries a traversal can need: the sentinel + one deferred sibling per level of the BVH.
     int32_t build_world(World& w, Aabb& bounds) {
-        std::vector<Item> top;
-        int inst_depth = 0;
-        for (const auto& path : w.paths) {
-            Group& g = w.groups[path];
-            if (path.empty()) {
-                for (auto& it : g.items) top.push_back(it);
-                continue;
-            }
-            Aabb ob;
-            BvhBuilder b(out.nodes, out.records, g.items);
-            int32_t root = b.build(ob);
-            inst_depth = std::max(inst_depth, b.depth);
-            Item inst;
-            std::memset(&inst.rec, 0, sizeof(inst.rec));
-            inst.rec.type = REC_INSTANCE;
-            inst.rec.a = root;
-            inst.rec.c = add_chain(g.chain);
-            inst.box.reset();
-            if (!g.items.empty()) {
-                for (int corner = 0; corner < 8; ++corner) {
-                    double p[3] = {(corner & 1) ? ob.hi[0] : ob.lo[0], (corner & 2) ? ob.hi[1] : ob.lo[1],
-                                   (corner & 4) ? ob.hi[2] : ob.lo[2]};
-                    to_world(g.chain, p);
-                    inst.box.grow_point(p);
-                }
-                // rotation arithmetic rounds: pad by a few ulps of the extent
-                for (int i = 0; i < 3; ++i) {
-                    double pad = 1e-12 * std::fmax(1.0, std::fmax(std::fabs(inst.box.lo[i]), std::fabs(inst.box.hi[i])));
-                    inst.box.lo[i] -= pad; inst.box.hi[i] += pad;
-                }
-            }
-            top.push_back(inst);
-        }
-        BvhBuilder b(out.nodes, out.records, top);
+        BvhBuilder b(out.nodes, out.records, w.items);
         int32_t root = b.build(bounds);
-        out.max_stack = std::max(out.max_stack, 1 + b.depth + 2 + inst_depth + 1);
+        out.max_stack = std::max(out.max_stack, 1 + b.depth + 1);
         // media: records outside every BVH + a bounds list (only the main world has any)
         for (auto& m : w.media) {
             DMedium dm;
@@ -698,7 +683,7 @@ void camera_view(const rtx_camera& d, const double background[3], CameraView& o)
 
 // ---------------------------------------------------------------------------
 // Invariant checker (host logic tests): every BVH reachable from the world root
-// (through instance and medium records) must contain its records.
+// (and from medium records) must contain its records, in world space.
 // ---------------------------------------------------------------------------
 namespace {
 struct Checker {
@@ -712,27 +697,55 @@ struct Checker {
             if (!((double)lo[i] <= b.lo[i] && (double)hi[i] >= b.hi[i])) return false;
         return true;
     }
+    // object -> world through the record's chain (composition of its ops; cs/sn/t map world -> object)
+    void to_world_point(int32_t chain, double p[3]) const {
+        if (chain == 0) return;
+        const DChain& c = fs.chains[(size_t)chain];
+        for (int k = c.len - 1; k >= 0; --k) {
+            const XformOp& op = fs.xforms[(size_t)(c.begin + k)];
+            if (op.kind == XF_TRANSLATE) {
+                p[0] += op.v[0]; p[1] += op.v[1]; p[2] += op.v[2];
+            } else {
+                double sn = op.v[0], cs = op.v[1];
+                double x = cs * p[0] + sn * p[2], z = -sn * p[0] + cs * p[2];
+                p[0] = x; p[2] = z;
+            }
+        }
+    }
+    // WORLD-space points the leaf box of a record must contain (its object-space extreme points, moved out)
     bool record_box(const Record& r, Aabb& b) {
         b.reset();
+        if (r.c < 0 || r.c >= (int32_t)fs.chains.size()) return false;
         static const int ax0[3] = {0, 0, 1}, ax1[3] = {1, 2, 2}, axk[3] = {2, 1, 0};
+        Aabb ob;
+        ob.reset();
         switch (r.type) {
             case REC_SPHERE:
-                for (int i = 0; i < 3; ++i) { b.lo[i] = r.d[i] - std::fabs(r.d[3]); b.hi[i] = r.d[i] + std::fabs(r.d[3]); }
-                return true;
-            case REC_MSPHERE:
-                for (int i = 0; i < 3; ++i) {  // at its own t0 (a point the bounds must contain when t0 is in the shutter)
-                    b.lo[i] = r.d[i] - std::fabs(r.d[6]); b.hi[i] = r.d[i] + std::fabs(r.d[6]);
-                }
-                return true;
-            case REC_RECT_XY: case REC_RECT_XZ: case REC_RECT_YZ: {
-                int p = r.type - REC_RECT_XY;
-                b.lo[ax0[p]] = std::fmin(r.d[0], r.d[1]); b.hi[ax0[p]] = std::fmax(r.d[0], r.d[1]);
-                b.lo[ax1[p]] = std::fmin(r.d[2], r.d[3]); b.hi[ax1[p]] = std::fmax(r.d[2], r.d[3]);
-                b.lo[axk[p]] = r.d[4]; b.hi[axk[p]] = r.d[4];
+            case REC_MSPHERE: {  // a moving sphere at its own t0 (a point the bounds must contain when t0 is in the shutter)
+                double c[3] = {r.d[0], r.d[1], r.d[2]};
+                double rad = std::fabs(r.type == REC_SPHERE ? r.d[3] : r.d[6]);
+                to_world_point(r.c, c);
+                for (int i = 0; i < 3; ++i) { b.lo[i] = c[i] - rad; b.hi[i] = c[i] + rad; }
                 return true;
             }
-            default: return false;  // instance / medium: checked through their own BVH
+            case REC_RECT_XY: case REC_RECT_XZ: case REC_RECT_YZ: {
+                int p = r.type - REC_RECT_XY;
+                ob.lo[ax0[p]] = std::fmin(r.d[0], r.d[1]); ob.hi[ax0[p]] = std::fmax(r.d[0], r.d[1]);
+                ob.lo[ax1[p]] = std::fmin(r.d[2], r.d[3]); ob.hi[ax1[p]] = std::fmax(r.d[2], r.d[3]);
+                ob.lo[axk[p]] = r.d[4]; ob.hi[axk[p]] = r.d[4];
+                break;
+            }
+            case REC_BOX:
+                for (int i = 0; i < 3; ++i) { ob.lo[i] = r.d[i]; ob.hi[i] = r.d[3 + i]; }
+                break;
+            default: return false;
         }
+        for (int corner = 0; corner < 8; ++corner) {
+            double p[3] = {(corner & 1) ? ob.hi[0] : ob.lo[0], (corner & 2) ? ob.hi[1] : ob.lo[1], (corner & 4) ? ob.hi[2] : ob.lo[2]};
+            to_world_point(r.c, p);
+            b.grow_point(p);
+        }
+        return true;
     }
     // returns the union of the float boxes of the subtree through `bounds_lo/hi`
     bool walk(int32_t ni, int depth, int& n_records) {
@@ -767,12 +780,14 @@ struct Checker {
                     Aabb b;
                     if (record_box(r, b)) {
                         if (!inside(lo, hi, b)) return fail("record not inside its leaf box");
-                    } else if (r.type == REC_INSTANCE) {
-                        if (r.c <= 0 || r.c >= (int)fs.chains.size()) return fail("instance chain out of range");
-                        const DChain& ch = fs.chains[(size_t)r.c];
-                        if (ch.begin < 0 || ch.len <= 0 || ch.begin + ch.len > (int)fs.xforms.size()) return fail("chain ops out of range");
-                        int sub = 0;
-                        if (!walk(r.a, depth + 1, sub)) return false;
+                        if (r.type == REC_BOX) {  // its six face records live outside every leaf
+                            if (r.a < 0 || r.a + 6 > (int32_t)fs.records.size()) return fail("box face records out of range");
+                            for (int k = 0; k < 6; ++k) {
+                                const Record& fr = fs.records[(size_t)(r.a + k)];
+                                if (fr.type < REC_RECT_XY || fr.type > REC_RECT_YZ || fr.c != r.c) return fail("box face record is not a rectangle of the box");
+                                if (rec_seen[(size_t)(r.a + k)]++) return fail("box face record referenced twice");
+                            }
+                        }
                     } else {
                         return fail("unknown record type");
                     }

@@ -205,30 +205,61 @@ struct Best {
 
 constexpr int kStackSize = kTraversalStack;
 constexpr int32_t kSentinel = (int32_t)0x80000000;       // bottom of a query's stack
-constexpr int32_t kLeaveInstance = (int32_t)0x80000001;  // pop: return to the query's own space
 
-// One geometric record (sphere / moving sphere / rectangle) against the ray (o, d) of its space.
+// One geometric record (sphere / moving sphere / rectangle / box) against the ray: the ray is pushed
+// through the record's wrapper chain first (Translate::hit / YRotate::hit, hittable.rs:600-604,687-692).
+// `hit_rec` is the record the hit record is built from (a box reports the rectangle of the face hit).
 // One copy of each intersection routine per kernel: code size is what the instruction cache sees.
 template <bool kCount>
-__device__ __forceinline__ bool test_geometry(const Record* rp, int32_t type, d3 o, d3 d, double time, double tmin, double tmax,
-                                              double& t, Tally<kCount>& tally) {
-    const double* q = rp->d;
+__device__ __forceinline__ bool test_geometry(const SceneView& sc, int32_t ri, int4 h, const RayD& ray, double tmin, double tmax,
+                                              double& t, int32_t& hit_rec, Tally<kCount>& tally) {
+    const double* q = sc.records[ri].d;
+    d3 o = ray.o, d = ray.d;
+    if (h.w != 0) to_space(sc, h.w, o, d);
     double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
-    if (type <= REC_MSPHERE) {
+    hit_rec = ri;
+    if (h.x <= REC_MSPHERE) {
         tally.sphere();
         d3 c = mk(a.x, a.y, b.x);
         double r = b.y;
-        if (type == REC_MSPHERE) {  // MovingSphere::center, hittable.rs:187-191
+        if (h.x == REC_MSPHERE) {  // MovingSphere::center, hittable.rs:187-191
             double2 e = __ldg(reinterpret_cast<const double2*>(q + 4)), g = __ldg(reinterpret_cast<const double2*>(q + 6));
-            double f = (time - g.y) * ldg_d(q + 8);
+            double f = (ray.time - g.y) * ldg_d(q + 8);
             c = mk(a.x + f * b.y, a.y + f * e.x, b.x + f * e.y);
             r = g.x;
         }
         return sphere_roots(o, d, c, r, tmin, tmax, t);
     }
     tally.rect();
+    if (h.x == REC_BOX) {
+        // Cube::hit = List::hit over six rectangles (hittable.rs:580-582): a line meets them where it enters and
+        // where it leaves the box, at the (k - o) / d each Rectangle::hit computes (:504); the closest one inside
+        // [tmin, tmax] is the entry face, or the exit face when the entry lies before tmin.
+        double2 e = __ldg(reinterpret_cast<const double2*>(q + 4));
+        const double lo[3] = {a.x, a.y, b.x}, hi[3] = {b.y, e.x, e.y};
+        double tn = -CUDART_INF, tf = CUDART_INF;
+        int fn = 0, ff = 0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            const double oa = comp(o, ax), da = comp(d, ax);
+            const double t0 = (lo[ax] - oa) / da, t1 = (hi[ax] - oa) / da;
+            const bool neg = t1 < t0;  // the ray runs from hi to lo on this axis
+            const double tnear = neg ? t1 : t0, tfar = neg ? t0 : t1;
+            const int base = ax == 0 ? 4 : (ax == 1 ? 2 : 0);  // Cube::new order: xy(min.z), xy(max.z), xz(min.y), xz(max.y), yz(min.x), yz(max.x)
+            if (tnear > tn) { tn = tnear; fn = base + (neg ? 1 : 0); }
+            if (tfar < tf) { tf = tfar; ff = base + (neg ? 0 : 1); }
+        }
+        if (!(tn <= tf)) return false;
+        double tt = tn;
+        int face = fn;
+        if (tn < tmin) { tt = tf; face = ff; }
+        if (tt < tmin || tt > tmax) return false;
+        t = tt;
+        hit_rec = h.y + face;
+        return true;
+    }
     double dd[5] = {a.x, a.y, b.x, b.y, ldg_d(q + 4)};
-    return rect_hit(o, d, type - REC_RECT_XY, dd, tmin, tmax, t);
+    return rect_hit(o, d, h.x - REC_RECT_XY, dd, tmin, tmax, t);
 }
 
 // One inner node: both child boxes against the ray; returns the next node to visit and pushes the
@@ -254,57 +285,32 @@ __device__ __forceinline__ int32_t node_step(const SceneView& sc, int32_t cur, c
 }
 
 // Closest hit over the BVH rooted at `root` for `ray` in [tmin, best.t]: plain while-while
-// traversal, instances entered by switching the ray's space inside the same loop. Used by the
-// fixed-ray kernel and by ConstantMedium boundary queries (the render kernel runs the batched
-// form of the same steps). `stack` is a per-thread array, `sp` the first free slot.
+// traversal in world space. Used by the fixed-ray kernel, the wavefront trace kernel and
+// ConstantMedium boundary queries. `stack` is a per-thread array, `sp` the first free slot.
 template <bool kCount>
 __device__ __forceinline__ void traverse_simple(const SceneView& sc, int32_t root, const RayD& ray, double tmin, Best& best,
                                                 int32_t* stack, int sp, Tally<kCount>& tally) {
     SlabRay s;
-    d3 o = ray.o, d = ray.d;
-    bool reslab = true;
+    make_slab(ray.o, ray.d, s);
     float tmin_f = __double2float_rd(tmin);
     float tmax_f = __double2float_ru(best.t);
-    int32_t cur_chain = 0;
     stack[sp++] = kSentinel;
     int32_t cur = root;
     while (true) {
-        if (reslab) {
-            make_slab(o, d, s);
-            reslab = false;
-        }
         while (cur >= 0) cur = node_step(sc, cur, s, tmin_f, tmax_f, stack, sp, tally);
         if (cur == kSentinel) break;
-        if (cur == kLeaveInstance) {
-            o = ray.o; d = ray.d;
-            reslab = true;
-            cur_chain = 0;
-            cur = stack[--sp];
-            continue;
-        }
         int32_t v = ~cur;
         int32_t first = v >> 4, count = v & 15;
         cur = stack[--sp];
         for (int32_t i = 0; i < count; ++i) {
-            const Record* rp = sc.records + first + i;
-            int4 h = __ldg(reinterpret_cast<const int4*>(rp));
-            if (h.x == REC_INSTANCE) {  // enter: re-express the ray (Translate/YRotate::hit), keep traversing in the same loop
-                tally.instance();
-                cur_chain = h.w;
-                o = ray.o; d = ray.d;
-                to_space(sc, cur_chain, o, d);
-                reslab = true;
-                stack[sp++] = cur;  // what we were about to visit next, resumed after the instance
-                stack[sp++] = kLeaveInstance;
-                cur = h.y;
-            } else if (h.x <= REC_RECT_YZ) {
-                double t;
-                if (test_geometry(rp, h.x, o, d, ray.time, tmin, best.t, t, tally)) {
-                    best.t = t;
-                    best.rec = first + i;
-                    best.chain = cur_chain;
-                    tmax_f = __double2float_ru(t);
-                }
+            int4 h = __ldg(reinterpret_cast<const int4*>(sc.records + first + i));
+            double t;
+            int32_t hit_rec;
+            if (test_geometry(sc, first + i, h, ray, tmin, best.t, t, hit_rec, tally)) {
+                best.t = t;
+                best.rec = hit_rec;
+                best.chain = h.w;
+                tmax_f = __double2float_ru(t);
             }
         }
     }
@@ -877,7 +883,7 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
     SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     Best best{0.0, -1, 0};
     float tmax_f = 0.f;
-    int32_t cur = kSentinel, pending = 0, cur_chain = 0;  // pending: a postponed leaf (leaf codes are negative; 0 = none)
+    int32_t cur = kSentinel, pending = 0;  // pending: a postponed leaf (leaf codes are negative; 0 = none)
     int sp = 0;
     Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
     PathColor pc{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
@@ -889,13 +895,13 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
         if (st == ST_TRAV && cur < 0) {
             if (cur == kSentinel) {
                 if (pending == 0) st = ST_SHADE;
-            } else if (cur != kLeaveInstance && pending == 0) {
+            } else if (pending == 0) {
                 pending = cur;  // postpone the leaf, keep traversing (speculatively: best.t is not shrunk yet)
                 cur = stack[--sp];
             }
         }
         const bool want_node = st == ST_TRAV && cur >= 0;
-        const bool want_leaf = st == ST_TRAV && cur < 0 && (pending != 0 || cur == kLeaveInstance);
+        const bool want_leaf = st == ST_TRAV && cur < 0 && pending != 0;
         const bool want_shade = st == ST_SHADE || st == ST_NEW;
         const int n_node = __popc(__ballot_sync(FULL, want_node));
         const int n_leaf = __popc(__ballot_sync(FULL, want_leaf));
@@ -915,7 +921,7 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
             for (int it = 0; it < a.node_burst; ++it) {
                 if (go) {
                     cur = node_step(a.sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
-                    if (cur < 0 && cur != kSentinel && cur != kLeaveInstance && pending == 0) {
+                    if (cur < 0 && cur != kSentinel && pending == 0) {
                         pending = cur;  // postpone the leaf, keep traversing
                         cur = stack[--sp];
                     }
@@ -926,43 +932,20 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
         } else if (s_leaf >= s_shade) {
             // ================= leaf phase =================
             if (want_leaf) {
-                d3 o = ray.o, d = ray.d;
-                bool reslab = false;
-                if (pending != 0) {
-                    if (cur_chain != 0) to_space(a.sc, cur_chain, o, d);
-                    int32_t v = ~pending;
-                    int32_t first = v >> 4, count = v & 15;
-                    pending = 0;
-                    for (int32_t i = 0; i < count; ++i) {
-                        const Record* rp = a.sc.records + first + i;
-                        int4 h = __ldg(reinterpret_cast<const int4*>(rp));
-                        if (h.x == REC_INSTANCE) {  // Translate / YRotate::hit: re-express the ray, descend
-                            tally.instance();
-                            cur_chain = h.w;
-                            o = ray.o; d = ray.d;
-                            to_space(a.sc, cur_chain, o, d);
-                            reslab = true;
-                            stack[sp++] = cur;
-                            stack[sp++] = kLeaveInstance;
-                            cur = h.y;
-                        } else if (h.x <= REC_RECT_YZ) {
-                            double t;
-                            if (test_geometry(rp, h.x, o, d, ray.time, 0.001, best.t, t, tally)) {
-                                best.t = t;
-                                best.rec = first + i;
-                                best.chain = cur_chain;
-                                tmax_f = __double2float_ru(t);
-                            }
-                        }
+                int32_t v = ~pending;
+                int32_t first = v >> 4, count = v & 15;
+                pending = 0;
+                for (int32_t i = 0; i < count; ++i) {
+                    int4 h = __ldg(reinterpret_cast<const int4*>(a.sc.records + first + i));
+                    double t;
+                    int32_t hit_rec;
+                    if (test_geometry(a.sc, first + i, h, ray, 0.001, best.t, t, hit_rec, tally)) {
+                        best.t = t;
+                        best.rec = hit_rec;
+                        best.chain = h.w;
+                        tmax_f = __double2float_ru(t);
                     }
                 }
-                if (cur == kLeaveInstance) {  // back to world space
-                    o = ray.o; d = ray.d;
-                    reslab = true;
-                    cur_chain = 0;
-                    cur = stack[--sp];
-                }
-                if (reslab) make_slab(o, d, sr);
             }
         } else {
             // ================= shade phase =================
@@ -1042,7 +1025,6 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
                 stack[sp++] = kSentinel;
                 cur = a.sc.world_root;
                 pending = 0;
-                cur_chain = 0;
                 st = ST_TRAV;
                 ++my_rays;
             }
@@ -1279,298 +1261,10 @@ __global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_kernel(Scene
     }
 }
 
-// Persistent form of the trace kernel: a warp keeps 32 rays in flight and a lane whose ray is done
-// writes its hit and takes the next slot from a global counter, so a long ray no longer holds 31
-// idle lanes (the one-slot-per-thread form runs at ~9 of 32 lanes: a warp lasts as long as its
-// longest ray). Three kinds of steps — BVH node steps (fp32), leaf events (f64 tests, instance
-// enter / leave) and fetches (write back, load the next ray, slab set-up) — are run one kind at a
-// time for all lanes waiting for that kind, chosen by vote; a lane that reaches a leaf postpones it
-// and keeps traversing speculatively.
-struct TraceTune {
-    int32_t w_node, w_leaf, w_fetch;  // vote weights
-    int32_t node_burst;               // node steps per vote, at most
-    int32_t speculate;                // 1: keep traversing with one leaf postponed
-};
-
-template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_persistent_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
-                                                                       TraceTune tune, unsigned long long* ray_count, Counters* counters) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    int32_t stack[kStackSize];
-    Tally<kCount> tally;
-    const float tmin_f = __double2float_rd(0.001);
-    // lane state: slot < 0 = no ray (wants a fetch); dry = the counter ran past n_slots
-    int slot = -1;
-    bool dry = false;
-    RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
-    SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    Best best{0.0, -1, 0};
-    float tmax_f = 0.f;
-    int32_t cur = kSentinel, pending = 0, cur_chain = 0;
-    int sp = 0;
-    unsigned int my_rays = 0;
-
-    while (true) {
-        // ---- cheap per-lane transitions, then the vote ----
-        bool finished = false;
-        if (slot >= 0 && cur < 0) {
-            if (cur == kSentinel) {
-                finished = pending == 0;
-            } else if (cur != kLeaveInstance && pending == 0) {
-                pending = cur;  // postpone the leaf, keep traversing (speculatively: best.t is not shrunk yet)
-                cur = stack[--sp];
-            }
-        }
-        // (without speculation a postponed leaf is tested before the lane takes another node step: the first
-        // leaf along an ordered traversal is usually the closest hit and prunes most of what is left)
-        const bool want_node = slot >= 0 && cur >= 0 && (pending == 0 || tune.speculate != 0);
-        const bool want_leaf = slot >= 0 && !want_node && (pending != 0 || cur == kLeaveInstance);
-        const bool want_fetch = (slot < 0 && !dry) || finished;
-        const int n_node = __popc(__ballot_sync(FULL, want_node));
-        const int n_leaf = __popc(__ballot_sync(FULL, want_leaf));
-        const int n_fetch = __popc(__ballot_sync(FULL, want_fetch));
-        if ((n_node | n_leaf | n_fetch) == 0) break;  // every lane is dry and idle
-        const int s_node = n_node * tune.w_node, s_leaf = n_leaf * tune.w_leaf, s_fetch = n_fetch * tune.w_fetch;
-
-        if (s_node >= s_leaf && s_node >= s_fetch) {
-            // ================= node phase =================
-            bool go = want_node;
-#pragma unroll 1
-            for (int it = 0; it < tune.node_burst; ++it) {
-                if (go) {
-                    cur = node_step(sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
-                    if (cur < 0 && cur != kSentinel && cur != kLeaveInstance && pending == 0) {
-                        pending = cur;
-                        cur = stack[--sp];
-                    }
-                    go = cur >= 0 && (pending == 0 || tune.speculate != 0);
-                }
-                if (2 * __popc(__ballot_sync(FULL, go)) < n_node) break;
-            }
-        } else if (s_leaf >= s_fetch) {
-            // ================= leaf phase =================
-            if (want_leaf) {
-                d3 o = ray.o, d = ray.d;
-                bool reslab = false;
-                if (pending != 0) {
-                    if (cur_chain != 0) to_space(sc, cur_chain, o, d);
-                    int32_t v = ~pending;
-                    int32_t first = v >> 4, count = v & 15;
-                    pending = 0;
-                    for (int32_t i = 0; i < count; ++i) {
-                        const Record* rp = sc.records + first + i;
-                        int4 h = __ldg(reinterpret_cast<const int4*>(rp));
-                        if (h.x == REC_INSTANCE) {  // Translate / YRotate::hit: re-express the ray, descend
-                            tally.instance();
-                            cur_chain = h.w;
-                            o = ray.o; d = ray.d;
-                            to_space(sc, cur_chain, o, d);
-                            reslab = true;
-                            stack[sp++] = cur;
-                            stack[sp++] = kLeaveInstance;
-                            cur = h.y;
-                        } else if (h.x <= REC_RECT_YZ) {
-                            double t;
-                            if (test_geometry(rp, h.x, o, d, ray.time, 0.001, best.t, t, tally)) {
-                                best.t = t;
-                                best.rec = first + i;
-                                best.chain = cur_chain;
-                                tmax_f = __double2float_ru(t);
-                            }
-                        }
-                    }
-                }
-                if (cur == kLeaveInstance) {  // back to world space
-                    o = ray.o; d = ray.d;
-                    reslab = true;
-                    cur_chain = 0;
-                    cur = stack[--sp];
-                }
-                if (reslab) make_slab(o, d, sr);
-            }
-        } else {
-            // ================= fetch phase =================
-            if (finished) {
-                if (best.rec >= 0) {  // closer than the medium candidate (if any) the shade kernel left there
-                    pool.best_t[slot] = best.t;
-                    pool.best_rec[slot] = best.rec;
-                    pool.best_chain[slot] = best.chain;
-                }
-                slot = -1;
-            }
-            // take slots until every fetching lane has an occupied one (or the counter runs dry)
-            unsigned need = __ballot_sync(FULL, want_fetch);
-            while (need != 0) {
-                const int leader = __ffs(need) - 1;
-                unsigned int base = 0;
-                if (lane == leader) base = atomicAdd(next_slot, (unsigned int)__popc(need));
-                base = __shfl_sync(FULL, base, leader);
-                const bool mine = ((need >> lane) & 1u) != 0;
-                if (mine) {
-                    const unsigned int idx = base + (unsigned int)__popc(need & lt_mask);
-                    if (idx >= (unsigned int)n_slots) {
-                        dry = true;
-                    } else if (pool.bounce[idx] >= 0) {
-                        slot = (int)idx;
-                    }
-                }
-                need = __ballot_sync(FULL, mine && slot < 0 && !dry);
-            }
-            if (want_fetch && slot >= 0) {
-                ray.o = mk(pool.ox[slot], pool.oy[slot], pool.oz[slot]);
-                ray.d = mk(pool.dx[slot], pool.dy[slot], pool.dz[slot]);
-                ray.time = pool.time[slot];
-                best.t = pool.best_t[slot];
-                best.rec = -1;
-                best.chain = 0;
-                make_slab(ray.o, ray.d, sr);
-                tmax_f = __double2float_ru(best.t);
-                sp = 0;
-                stack[sp++] = kSentinel;
-                cur = sc.world_root;
-                pending = 0;
-                cur_chain = 0;
-                ++my_rays;
-            }
-        }
-    }
-    if (ray_count) {
-        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(FULL, my_rays, off);
-        if (lane == 0 && my_rays) atomicAdd(ray_count, (unsigned long long)my_rays);
-    }
-    if constexpr (kCount) {
-        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
-        if (lane == 0) {
-            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
-            atomicAdd(&counters->box_tests, 2ull * vals[0]);
-            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
-            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
-            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
-        }
-    }
-}
-
-// Persistent while-while form: lanes refill at the top of the loop (one warp-aggregated atomic), then
-// every lane walks down to its next leaf on its own and tests it. No votes inside the walk.
-template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_refill_kernel(SceneView sc, PathPool pool, int n_slots, unsigned int* next_slot,
-                                                                   unsigned long long* ray_count, Counters* counters) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    int32_t stack[kStackSize];
-    Tally<kCount> tally;
-    const float tmin_f = __double2float_rd(0.001);
-    int slot = -1;
-    bool dry = false;
-    RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
-    d3 o = ray.o, d = ray.d;  // the ray in the space being traversed
-    SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    Best best{0.0, -1, 0};
-    float tmax_f = 0.f;
-    int32_t cur = kSentinel, cur_chain = 0;
-    int sp = 0;
-    unsigned int my_rays = 0;
-    while (true) {
-        // ---- refill ----
-        unsigned need = __ballot_sync(FULL, slot < 0 && !dry);
-        const bool fetching = ((need >> lane) & 1u) != 0;
-        while (need != 0) {
-            const int leader = __ffs(need) - 1;
-            unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(next_slot, (unsigned int)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            const bool mine = ((need >> lane) & 1u) != 0;
-            if (mine) {
-                const unsigned int idx = base + (unsigned int)__popc(need & lt_mask);
-                if (idx >= (unsigned int)n_slots) dry = true;
-                else if (pool.bounce[idx] >= 0) slot = (int)idx;
-            }
-            need = __ballot_sync(FULL, mine && slot < 0 && !dry);
-        }
-        if (fetching && slot >= 0) {
-            ray.o = mk(pool.ox[slot], pool.oy[slot], pool.oz[slot]);
-            ray.d = mk(pool.dx[slot], pool.dy[slot], pool.dz[slot]);
-            ray.time = pool.time[slot];
-            o = ray.o; d = ray.d;
-            best.t = pool.best_t[slot];
-            best.rec = -1;
-            best.chain = 0;
-            make_slab(o, d, sr);
-            tmax_f = __double2float_ru(best.t);
-            sp = 0;
-            stack[sp++] = kSentinel;
-            cur = sc.world_root;
-            cur_chain = 0;
-            ++my_rays;
-        }
-        if (__all_sync(FULL, slot < 0)) break;
-        if (slot >= 0) {
-            while (cur >= 0) cur = node_step(sc, cur, sr, tmin_f, tmax_f, stack, sp, tally);
-            if (cur == kSentinel) {
-                if (best.rec >= 0) {
-                    pool.best_t[slot] = best.t;
-                    pool.best_rec[slot] = best.rec;
-                    pool.best_chain[slot] = best.chain;
-                }
-                slot = -1;
-            } else if (cur == kLeaveInstance) {
-                o = ray.o; d = ray.d;
-                make_slab(o, d, sr);
-                cur_chain = 0;
-                cur = stack[--sp];
-            } else {
-                int32_t v = ~cur;
-                int32_t first = v >> 4, count = v & 15;
-                cur = stack[--sp];
-                for (int32_t i = 0; i < count; ++i) {
-                    const Record* rp = sc.records + first + i;
-                    int4 h = __ldg(reinterpret_cast<const int4*>(rp));
-                    if (h.x == REC_INSTANCE) {
-                        tally.instance();
-                        cur_chain = h.w;
-                        o = ray.o; d = ray.d;
-                        to_space(sc, cur_chain, o, d);
-                        make_slab(o, d, sr);
-                        stack[sp++] = cur;
-                        stack[sp++] = kLeaveInstance;
-                        cur = h.y;
-                    } else if (h.x <= REC_RECT_YZ) {
-                        double t;
-                        if (test_geometry(rp, h.x, o, d, ray.time, 0.001, best.t, t, tally)) {
-                            best.t = t;
-                            best.rec = first + i;
-                            best.chain = cur_chain;
-                            tmax_f = __double2float_ru(t);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (ray_count) {
-        for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(FULL, my_rays, off);
-        if (lane == 0 && my_rays) atomicAdd(ray_count, (unsigned long long)my_rays);
-    }
-    if constexpr (kCount) {
-        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
-        if (lane == 0) {
-            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
-            atomicAdd(&counters->box_tests, 2ull * vals[0]);
-            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
-            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
-            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
-        }
-    }
-}
+// (Two persistent forms of the trace kernel — warp-voted node / leaf / fetch phases, and refill at the top
+// of a while-while loop — were measured in round 1 at equal registers and lost to the form above:
+// 365 M and 400 M vs 413 M path samples/s on scene 9. DESIGN.md §4 has the numbers; the code is in the
+// history, commit "Wavefront defaults ...".)
 
 // color(.., depth = 0) is black without tracing anything (main.rs:27-29): count the samples only
 __global__ void add_black_samples_kernel(float4* __restrict__ accum, int n_pixels, float count) {
