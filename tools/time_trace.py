@@ -33,3 +33,11 @@ ter = RY.secondary_rays(h2, sec, rng)
 run(ter, "tertiary")
 perm = rng.permutation(ter.shape[0])
 run(ter[perm], "tertiary shuffled")
+# --- coherence experiments: the same tertiary rays in different orders ---
+d = ter["direction"]
+run(ter[np.argsort(d[:, 1] > 0, kind="stable")], "tertiary sorted by sign(dy)")
+run(ter[np.argsort(d[:, 1] / np.linalg.norm(d, axis=1))], "tertiary sorted by dy/|d|")
+octant = (d[:, 0] > 0).astype(int) | ((d[:, 1] > 0).astype(int) << 1) | ((d[:, 2] > 0).astype(int) << 2)
+run(ter[np.argsort(octant, kind="stable")], "tertiary sorted by octant")
+h3 = run(ter, "tertiary again")
+run(ter[np.argsort(np.where(h3["prim_id"] < 0, 1e30, h3["t"]))], "tertiary sorted by hit distance (oracle-ish)")
