@@ -469,6 +469,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     CU(cudaMemsetAsync(c->d_next_item, 0, sizeof(unsigned long long), c->stream));
     float4* acc = reinterpret_cast<float4*>(d_accum);
     const unsigned grid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
+    const unsigned sgrid = (unsigned)(slots / rtx::kShadeBlock);
     const int batch = c->wf_batch;
     size_t prof_used = 0;
     // every kProfStride-th iteration is bracketed (events between back-to-back launches cost ~10 % when every
@@ -497,12 +498,12 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             prof_now = c->profiling && (iteration++ % kProfStride) == 0;
             CU(prof_mark());
             if (counted) {
-                rtx::wf_shade_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
+                rtx::wf_shade_kernel<true><<<sgrid, rtx::kShadeBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
                 CU(prof_mark());
                 CU(prof_mark());
                 rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
             } else {
-                rtx::wf_shade_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a, acc, active, nullptr);
+                rtx::wf_shade_kernel<false><<<sgrid, rtx::kShadeBlock, 0, c->stream>>>(a, acc, active, nullptr);
                 CU(prof_mark());
                 CU(prof_mark());
                 rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);

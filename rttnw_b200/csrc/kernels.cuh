@@ -1078,7 +1078,11 @@ struct WfArgs {
     unsigned long long* next_item;    // global dispenser of path samples
 };
 
-constexpr int kWfBlock = 128;
+constexpr int kWfBlock = 128;   // trace kernel CTA; the pool size is a multiple of it
+#ifndef WF_SHADE_BLOCK
+#define WF_SHADE_BLOCK 128
+#endif
+constexpr int kShadeBlock = WF_SHADE_BLOCK;  // shade kernel CTA (divides kWfBlock)
 #ifndef WF_TRACE_MINB
 #define WF_TRACE_MINB 8
 #endif
@@ -1094,18 +1098,18 @@ constexpr int kWfBlock = 128;
 //      thread that owns the slot through shared memory;
 //   3. every thread that now has a ray — scattered or new — runs the medium pre-pass and writes its slot.
 template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock, WF_SHADE_MINB) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
+__global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBlock)) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < a.n_slots;
-    __shared__ int s_queue[kWfBlock];
+    __shared__ int s_queue[kShadeBlock];
     __shared__ int s_count;
     __shared__ unsigned long long s_base;
-    __shared__ double s_ray[7][kWfBlock];
-    __shared__ uint32_t s_pix[2][kWfBlock];
-    __shared__ unsigned char s_staged[kWfBlock];
+    __shared__ double s_ray[7][kShadeBlock];
+    __shared__ uint32_t s_pix[2][kShadeBlock];
+    __shared__ unsigned char s_staged[kShadeBlock];
     int32_t stack[kStackSize];  // only a ConstantMedium with a general boundary traverses here
     Tally<kCount> tally;
     if (tid == 0) s_count = 0;
