@@ -2,11 +2,18 @@
 // Same positional argument, same usage text, same stdout lines, writes image.png (RGBA8) in the
 // CWD and reads assets/earth.png relative to it. Optional flags default to the reference values:
 //   --spp N  --width W  --height H  --seed S  --scene-seed S  --gpus N  --out PATH  --chunk N
+//   --checkpoint PATH [--checkpoint-every K]  --resume PATH  --stop-after-chunks N
+// Checkpoint / resume (the reference keeps pixels in RAM until the final save_buffer, main.rs:202-231, so a
+// killed 10k-spp render loses everything): after every K chunks each GPU writes its fp32 accumulator and the
+// next sample index it would render to PATH.<gpu>; --resume reloads them (same scene, size, spp, seed, gpus)
+// and carries on. Samples are keyed by their global index, so a resumed image equals an uninterrupted one up
+// to fp32 summation order.
 // With --gpus N one host thread drives each device; samples are sharded by global sample index
 // and rank 0 sums the peers' accumulators over peer-mapped memory in the tonemap kernel.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -37,8 +44,35 @@ struct Rank {
     int rc = 0;
 };
 
+struct CheckpointHeader {  // little-endian, followed by width * height float4
+    char magic[8];         // "RTXACC1"
+    int32_t scene, width, height, spp_total, gpus, rank, next_sample, max_depth;
+    uint64_t seed, scene_seed;
+};
+
+static bool write_checkpoint(const std::string& path, const CheckpointHeader& h, const std::vector<float>& acc) {
+    std::string tmp = path + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(acc.data(), sizeof(float), acc.size(), f) == acc.size();
+    ok = std::fclose(f) == 0 && ok;
+    return ok && std::rename(tmp.c_str(), path.c_str()) == 0;  // never leaves a torn file behind
+}
+static bool read_checkpoint(const std::string& path, CheckpointHeader& h, std::vector<float>& acc) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "RTXACC1", 8) == 0 && h.width > 0 && h.height > 0;
+    if (ok) {
+        acc.resize((size_t)h.width * h.height * 4);
+        ok = std::fread(acc.data(), sizeof(float), acc.size(), f) == acc.size();
+    }
+    std::fclose(f);
+    return ok;
+}
+
 int main(int argc, char** argv) {
-    int scene = -1, spp = -1, width = -1, height = -1, gpus = 1, chunk = 256;
+    int scene = -1, spp = -1, width = -1, height = -1, gpus = 1, chunk = 256, ckpt_every = 1, stop_after = -1;
+    std::string ckpt_path, resume_path;
     unsigned long long seed = 1, scene_seed = 0;
     bool have_scene_seed = false;
     std::string out = "image.png";
@@ -56,6 +90,10 @@ int main(int argc, char** argv) {
         else if (a == "--seed") seed = std::strtoull(next("--seed"), nullptr, 0);
         else if (a == "--scene-seed") { scene_seed = std::strtoull(next("--scene-seed"), nullptr, 0); have_scene_seed = true; }
         else if (a == "--out") out = next("--out");
+        else if (a == "--checkpoint") ckpt_path = next("--checkpoint");
+        else if (a == "--checkpoint-every") ckpt_every = std::atoi(next("--checkpoint-every"));
+        else if (a == "--resume") resume_path = next("--resume");
+        else if (a == "--stop-after-chunks") stop_after = std::atoi(next("--stop-after-chunks"));
         else if (scene < 0 && !a.empty() && a[0] != '-') {
             char* end = nullptr;
             long v = std::strtol(a.c_str(), &end, 10);
@@ -91,19 +129,51 @@ int main(int argc, char** argv) {
         if (!chk(rtx_malloc(k.ctx, bytes, (void**)&k.accum))) return;
         if (!chk(rtx_memset_zero(k.ctx, k.accum, bytes))) return;
         int begin = (int)((long long)r * spp / gpus), end = (int)((long long)(r + 1) * spp / gpus);
+        CheckpointHeader hdr;
+        std::memset(&hdr, 0, sizeof(hdr));
+        std::memcpy(hdr.magic, "RTXACC1", 8);
+        hdr.scene = scene; hdr.width = width; hdr.height = height; hdr.spp_total = spp; hdr.gpus = gpus; hdr.rank = r;
+        hdr.max_depth = def.max_depth; hdr.seed = seed; hdr.scene_seed = scene_seed;
+        std::vector<float> host_acc;
+        if (!resume_path.empty()) {
+            CheckpointHeader got;
+            std::string path = resume_path + "." + std::to_string(r);
+            if (!read_checkpoint(path, got, host_acc) || got.scene != scene || got.width != width || got.height != height ||
+                got.spp_total != spp || got.gpus != gpus || got.rank != r || got.seed != seed || got.scene_seed != scene_seed ||
+                got.max_depth != def.max_depth || got.next_sample < begin || got.next_sample > end) {
+                std::fprintf(stderr, "gpu %d: %s is not a checkpoint of this render\n", r, path.c_str());
+                k.rc = 1;
+                return;
+            }
+            if (!chk(rtx_memcpy_h2d(k.ctx, k.accum, host_acc.data(), bytes))) return;
+            begin = got.next_sample;
+        }
+        int chunks_done = 0;
         for (int b = begin; b < end; b += chunk) {
             rtx_render_params p;
             std::memset(&p, 0, sizeof(p));
             p.width = width; p.height = height; p.spp_begin = b; p.spp_count = (end - b < chunk) ? end - b : chunk;
             p.max_depth = def.max_depth; p.seed = seed;
             if (!chk(rtx_render(k.ctx, k.scene, &p, k.accum, nullptr))) return;
+            ++chunks_done;
+            if (!ckpt_path.empty() && (chunks_done % (ckpt_every < 1 ? 1 : ckpt_every) == 0 || b + chunk >= end)) {
+                host_acc.resize(bytes / sizeof(float));
+                if (!chk(rtx_memcpy_d2h(k.ctx, host_acc.data(), k.accum, bytes))) return;  // ordered after the render on the ctx stream
+                hdr.next_sample = b + p.spp_count;
+                if (!write_checkpoint(ckpt_path + "." + std::to_string(r), hdr, host_acc)) {
+                    std::fprintf(stderr, "gpu %d: cannot write checkpoint %s\n", r, ckpt_path.c_str());
+                    k.rc = 1;
+                    return;
+                }
+            }
+            if (stop_after >= 0 && chunks_done >= stop_after) { k.rc = 3; return; }  // simulated interruption (tests)
         }
         chk(rtx_ctx_sync(k.ctx));
     };
     std::vector<std::thread> th;
     for (int r = 0; r < gpus; ++r) th.emplace_back(worker, r);
     for (auto& t : th) t.join();
-    for (auto& k : ranks) if (k.rc != 0) return 1;
+    for (auto& k : ranks) if (k.rc != 0) return k.rc == 3 ? 3 : 1;
 
     // combine on rank 0: peers' accumulators are read over NVLink by the fused reduce+tonemap kernel
     std::vector<uint8_t> rgba((size_t)width * height * 4);

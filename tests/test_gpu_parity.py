@@ -376,3 +376,53 @@ def test_reduce_tonemap_kernel_single_device(ctx):
     ctx.sync()
     assert np.array_equal(out.cpu().numpy(), expect)
     assert torch.allclose(accs[0], total)
+
+
+# ---------------------------------------------------------------------------
+# the CLI (`cargo run --release -- <scene>`, src/main.rs:236-258)
+# ---------------------------------------------------------------------------
+CLI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rttnw_b200", "lib", "rttnw")
+
+
+def run_cli(args, cwd):
+    import subprocess
+    return subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=300)
+
+
+def test_cli_writes_image_png_like_the_reference(tmp_path, ctx):
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.symlink(os.path.join(root, "assets"), tmp_path / "assets")  # ImageTexture::new("assets/earth.png") is CWD-relative
+    r = run_cli([4, "--spp", 16, "--width", 80, "--height", 45], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines()[0] == "Scene number: 4" and "Running scene earth" in r.stdout
+    img = np.asarray(Image.open(tmp_path / "image.png"))
+    assert img.shape == (45, 80, 4) and (img[..., 3] == 255).all()
+    # the same render through the library, same seeds: the same pixels (up to the order of the fp32 atomics)
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(4))
+    acc = gsc.new_accum(80, 45)
+    gsc.render_into(acc, 0, 16, seed=1)
+    assert np.abs(gsc.tonemap(acc).astype(int) - img.astype(int)).max() <= 1
+    # usage and unknown scenes behave like main.rs:238-251,179-182
+    r = run_cli([], tmp_path)
+    assert r.returncode != 0 and "Usage:" in r.stderr and "9: final_scene" in r.stderr
+    assert run_cli([12], tmp_path).returncode != 0
+
+
+def test_cli_checkpoint_and_resume(tmp_path):
+    """a killed render is resumed from its fp32 accumulator; samples are keyed by their
+    global index, so the result equals the uninterrupted render up to fp32 summation order."""
+    from PIL import Image
+    common = [7, "--spp", 48, "--width", 64, "--height", 64, "--chunk", 8]
+    r = run_cli(common + ["--out", "full.png"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    r = run_cli(common + ["--out", "part.png", "--checkpoint", "ck", "--stop-after-chunks", 3], tmp_path)
+    assert r.returncode == 3 and os.path.exists(tmp_path / "ck.0") and not os.path.exists(tmp_path / "part.png")
+    r = run_cli(common + ["--out", "resumed.png", "--resume", "ck", "--checkpoint", "ck"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    full = np.asarray(Image.open(tmp_path / "full.png")).astype(int)
+    resumed = np.asarray(Image.open(tmp_path / "resumed.png")).astype(int)
+    assert np.abs(full - resumed).max() <= 1
+    # a checkpoint of another render is refused
+    r = run_cli([7, "--spp", 64, "--width", 64, "--height", 64, "--chunk", 8, "--resume", "ck"], tmp_path)
+    assert r.returncode == 1 and "not a checkpoint of this render" in r.stderr
