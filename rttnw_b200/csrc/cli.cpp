@@ -119,12 +119,19 @@ int main(int argc, char** argv) {
     rtx_scene_desc* desc = nullptr;
     RTX(rtx_builtin_scene(scene, scene_seed, nullptr, &desc));
 
+    const bool verbose = std::getenv("RTTNW_VERBOSE") != nullptr;
+    auto lap = [&](const char* what) {
+        if (verbose) std::fprintf(stderr, "[%8.3f s] %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
+    };
+    lap("scene description built");
     std::vector<Rank> ranks((size_t)gpus);
     auto worker = [&](int r) {
         Rank& k = ranks[(size_t)r];
         auto chk = [&](int rc) { if (rc != RTX_OK && k.rc == 0) { k.rc = rc; std::fprintf(stderr, "gpu %d: %s\n", r, rtx_last_error()); } return rc == RTX_OK; };
         if (!chk(rtx_ctx_create(r, nullptr, &k.ctx))) return;
+        if (r == 0) lap("context created");
         if (!chk(rtx_scene_create(k.ctx, desc, &k.scene))) return;
+        if (r == 0) lap("scene uploaded");
         size_t bytes = (size_t)width * height * 4 * sizeof(float);
         if (!chk(rtx_malloc(k.ctx, bytes, (void**)&k.accum))) return;
         if (!chk(rtx_memset_zero(k.ctx, k.accum, bytes))) return;
@@ -169,6 +176,7 @@ int main(int argc, char** argv) {
             if (stop_after >= 0 && chunks_done >= stop_after) { k.rc = 3; return; }  // simulated interruption (tests)
         }
         chk(rtx_ctx_sync(k.ctx));
+        if (r == 0) lap("render finished");
     };
     std::vector<std::thread> th;
     for (int r = 0; r < gpus; ++r) th.emplace_back(worker, r);
@@ -183,7 +191,9 @@ int main(int argc, char** argv) {
     for (int r = 1; r < gpus; ++r) peers.push_back(ranks[(size_t)r].accum);
     RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.empty() ? nullptr : peers.data(), (int)peers.size(), width, height, d_rgba));
     RTX(rtx_memcpy_d2h(ranks[0].ctx, rgba.data(), d_rgba, rgba.size()));
+    lap("frame on the host");
     RTX(rtx_png_write_rgba8(out.c_str(), width, height, rgba.data()));  // image::save_buffer("image.png", ..), main.rs:231
+    lap("png written");
     rtx_free(ranks[0].ctx, d_rgba);
     for (auto& k : ranks) {
         rtx_free(k.ctx, k.accum);
