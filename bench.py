@@ -410,7 +410,8 @@ def run_ours(args):
                             "(latency / issue slots are: see profiles/)" % (info["device_bytes"] / 1e6)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64 geometry / f32 BVH boxes, shading and accumulation", "data": "synthetic",
+                "dtype": "f64", "dtype_note": "f64 rays, primitive tests, hit points and scatter directions; fp32 BVH boxes (conservative), "
+                "textures, throughput and accumulation", "data": "synthetic",
                 "config": config(args, d, w, h, {"combine": combine, "bvh_nodes": info["bvh_nodes"], "records": info["records"],
                                                  "scene_bytes": info["device_bytes"]}),
                 "rays_per_sec": rays_total / (total_ms * 1e-3), "rays_per_sample": rays_total / samples_total,
