@@ -74,6 +74,8 @@ struct rtx_ctx {
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
     int wf_batch = 8;
     unsigned long long launches = 0;  // kernels launched by this context (rtx_ctx_kernel_launches)
+    uint8_t* h_stage = nullptr;       // pinned staging buffer of rtx_scene_create (every H2D copy leaves from here)
+    size_t stage_bytes = 0;
     // optional per-kernel timing of the wavefront driver (rtx_ctx_set_profiling): CUDA events around every launch
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // grows on demand; [4 * iteration + {0,1,2,3}] = shade begin/end, trace begin/end
@@ -157,6 +159,7 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     cudaFree(c->d_next_item);
     cudaFree(c->d_active);
     if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& e : c->batch_done)
         if (e) cudaEventDestroy(e);
     for (auto e : c->prof_events) cudaEventDestroy(e);
@@ -204,6 +207,29 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->device = c->device;
     auto bail = [&](int code) { rtx_scene_destroy(s); return code; };
 
+    // pinned staging: the flattened arena and the image texels are copied H2D from page-locked memory
+    size_t image_bytes = 0;
+    for (int i = 0; i < desc->n_images; ++i)
+        if (desc->images[i].rgba && desc->images[i].width > 0 && desc->images[i].height > 0)
+            image_bytes += ((size_t)desc->images[i].width * (size_t)desc->images[i].height * 4 + 255) & ~(size_t)255;
+    auto stage_reserve = [&](size_t bytes) -> cudaError_t {
+        if (bytes <= c->stage_bytes) return cudaSuccess;
+        if (c->h_stage) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->stage_bytes = 0; }
+        cudaError_t err = cudaMallocHost(&c->h_stage, bytes);
+        if (err == cudaSuccess) c->stage_bytes = bytes;
+        return err;
+    };
+    const size_t arena_bound = fs.nodes.size() * sizeof(rtx::BvhNode) + fs.records.size() * sizeof(rtx::Record) +
+                               fs.xforms.size() * sizeof(rtx::XformOp) + fs.chains.size() * sizeof(rtx::DChain) +
+                               fs.materials.size() * sizeof(rtx::DMaterial) + fs.textures.size() * sizeof(rtx::DTexture) +
+                               fs.perlins.size() * sizeof(rtx::DPerlin) + (size_t)desc->n_images * sizeof(rtx::DImage) +
+                               fs.media.size() * sizeof(rtx::DMedium) + 16 * 256;
+    {
+        cudaError_t e = stage_reserve(image_bytes + arena_bound);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost(staging)"));
+    }
+    size_t stage_used = 0;
+
     // images -> point-sampled texture objects (ImageTexture, texture.rs:61-107)
     std::vector<rtx::DImage> dimages((size_t)desc->n_images);
     for (int i = 0; i < desc->n_images; ++i) {
@@ -241,7 +267,11 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
             if (e != cudaSuccess) { cudaFreeArray(slot.arr); return bail(cuda_fail(e, "cudaCreateTextureObject")); }
         }
         s->images.push_back(slot);
-        e = cudaMemcpy2DToArrayAsync(slot.arr, 0, 0, im.rgba, (size_t)im.width * 4, (size_t)im.width * 4, (size_t)im.height,
+        const size_t nbytes = (size_t)im.width * (size_t)im.height * 4;
+        uint8_t* staged = c->h_stage + stage_used;
+        std::memcpy(staged, im.rgba, nbytes);
+        stage_used += (nbytes + 255) & ~(size_t)255;
+        e = cudaMemcpy2DToArrayAsync(slot.arr, 0, 0, staged, (size_t)im.width * 4, (size_t)im.width * 4, (size_t)im.height,
                                      cudaMemcpyHostToDevice, c->stream);
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy2DToArray"));
         cudaTextureObject_t tex = slot.tex;
@@ -260,8 +290,10 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     size_t off_images = align(off_perlins + fs.perlins.size() * sizeof(rtx::DPerlin));
     size_t off_media = align(off_images + dimages.size() * sizeof(rtx::DImage));
     size_t total = align(off_media + fs.media.size() * sizeof(rtx::DMedium)) + 256;
-    std::vector<uint8_t> host(total, 0);
-    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(host.data() + off, src, bytes); };
+    if (total > arena_bound) return bail(fail(RTX_ERR_NOMEM, "internal: arena larger than its bound"));
+    uint8_t* host = c->h_stage + stage_used;
+    std::memset(host, 0, total);
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(host + off, src, bytes); };
     put(off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(rtx::BvhNode));
     put(off_records, fs.records.data(), fs.records.size() * sizeof(rtx::Record));
     put(off_xforms, fs.xforms.data(), fs.xforms.size() * sizeof(rtx::XformOp));
@@ -290,8 +322,8 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
         s->arena_capacity = total;
     }
     s->arena_bytes = total;
-    e = cudaMemcpyAsync(s->d_arena, host.data(), total, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // `host` dies with this frame
+    e = cudaMemcpyAsync(s->d_arena, host, total, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the staging buffer is reused by the next call
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(scene)"));
     uint8_t* base = (uint8_t*)s->d_arena;
     s->view.nodes = (const rtx::BvhNode*)(base + off_nodes);
