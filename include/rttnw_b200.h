@@ -229,6 +229,10 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out);
 int rtx_ctx_destroy(rtx_ctx* ctx);
 int rtx_ctx_sync(rtx_ctx* ctx);
 void* rtx_ctx_stream(rtx_ctx* ctx);
+/* Which builder makes the BVH over the world in rtx_scene_create (replaces BvhTree::new, hittable.rs:260-321; the
+ * tree's topology is not part of the contract, only the closest-hit answers): 0 = host, binned SAH (default, the
+ * better trees), 1 = device, Morton-code LBVH (for scenes large enough that the host build is the bottleneck). */
+int rtx_ctx_set_bvh_builder(rtx_ctx* ctx, int kind);
 /* number of CUDA kernels this context has launched so far (bookkeeping for benchmarks) */
 int rtx_ctx_kernel_launches(rtx_ctx* ctx, unsigned long long* out);
 /* Per-kernel timing of rtx_render (benchmark bookkeeping): when on, the shade / trace launches of

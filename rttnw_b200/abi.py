@@ -110,6 +110,7 @@ SIGNATURES = {
     "rtx_ctx_destroy": (C.c_int, [_P]),
     "rtx_ctx_sync": (C.c_int, [_P]),
     "rtx_ctx_stream": (_P, [_P]),
+    "rtx_ctx_set_bvh_builder": (C.c_int, [_P, C.c_int]),
     "rtx_ctx_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rtx_ctx_set_profiling": (C.c_int, [_P, C.c_int]),
     "rtx_ctx_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),

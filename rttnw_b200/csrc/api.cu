@@ -13,6 +13,7 @@
 #include "../../include/rttnw_b200.h"
 #include "flatten.hpp"
 #include "kernels.cuh"
+#include "lbvh.cuh"
 #include "scene_api.hpp"
 
 namespace {
@@ -74,6 +75,7 @@ struct rtx_ctx {
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
     int wf_batch = 8;
     unsigned long long launches = 0;  // kernels launched by this context (rtx_ctx_kernel_launches)
+    int bvh_builder = 0;              // 0: host binned SAH (default), 1: device LBVH (rtx_ctx_set_bvh_builder, RTX_BVH=lbvh)
     uint8_t* h_stage = nullptr;       // pinned staging buffer of rtx_scene_create (every H2D copy leaves from here)
     size_t stage_bytes = 0;
     // optional per-kernel timing of the wavefront driver (rtx_ctx_set_profiling): CUDA events around every launch
@@ -142,6 +144,7 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->pool_slots_wanted = env_int("RTX_WF_SLOTS", c->pool_slots_wanted);
     c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
+    if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : 0;
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -188,6 +191,11 @@ int rtx_ctx_profile_read(rtx_ctx* c, double* shade_ms, double* trace_ms, unsigne
     if (reset) { c->prof_shade_ms = c->prof_trace_ms = 0; c->prof_iterations = 0; }
     return RTX_OK;
 }
+int rtx_ctx_set_bvh_builder(rtx_ctx* c, int kind) {
+    if (!c || kind < 0 || kind > 1) return fail(RTX_ERR_INVALID, "bad argument");
+    c->bvh_builder = kind;
+    return RTX_OK;
+}
 int rtx_ctx_kernel_launches(rtx_ctx* c, unsigned long long* out) {
     if (!c || !out) return fail(RTX_ERR_INVALID, "NULL argument");
     *out = c->launches;
@@ -201,7 +209,10 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     CU(cudaSetDevice(c->device));
     rtx::FlatScene fs;
     std::string err;
-    if (!rtx::flatten_scene(*desc, fs, err)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    if (!rtx::flatten_scene(*desc, fs, err, c->bvh_builder == 1)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    // nodes the device builder will add behind the host-built ones (medium boundaries), and its box upload
+    const size_t host_nodes = fs.nodes.size();
+    const size_t lbvh_nodes = fs.world_deferred ? (size_t)fs.world_count - 1 : 0;
     rtx_scene* s = new (std::nothrow) rtx_scene();
     if (!s) return fail(RTX_ERR_NOMEM, "out of host memory");
     s->device = c->device;
@@ -219,7 +230,8 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
         if (err == cudaSuccess) c->stage_bytes = bytes;
         return err;
     };
-    const size_t arena_bound = fs.nodes.size() * sizeof(rtx::BvhNode) + fs.records.size() * sizeof(rtx::Record) +
+    const size_t arena_bound = (host_nodes + lbvh_nodes) * sizeof(rtx::BvhNode) + fs.world_boxes.size() * sizeof(float) +
+                               fs.records.size() * sizeof(rtx::Record) +
                                fs.xforms.size() * sizeof(rtx::XformOp) + fs.chains.size() * sizeof(rtx::DChain) +
                                fs.materials.size() * sizeof(rtx::DMaterial) + fs.textures.size() * sizeof(rtx::DTexture) +
                                fs.perlins.size() * sizeof(rtx::DPerlin) + (size_t)desc->n_images * sizeof(rtx::DImage) +
@@ -281,7 +293,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     // one arena, every array 256-byte aligned
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off_nodes = 0;
-    size_t off_records = align(off_nodes + fs.nodes.size() * sizeof(rtx::BvhNode));
+    size_t off_records = align(off_nodes + (host_nodes + lbvh_nodes) * sizeof(rtx::BvhNode));
     size_t off_xforms = align(off_records + fs.records.size() * sizeof(rtx::Record));
     size_t off_chains = align(off_xforms + fs.xforms.size() * sizeof(rtx::XformOp));
     size_t off_mats = align(off_chains + fs.chains.size() * sizeof(rtx::DChain));
@@ -289,7 +301,8 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     size_t off_perlins = align(off_texs + fs.textures.size() * sizeof(rtx::DTexture));
     size_t off_images = align(off_perlins + fs.perlins.size() * sizeof(rtx::DPerlin));
     size_t off_media = align(off_images + dimages.size() * sizeof(rtx::DImage));
-    size_t total = align(off_media + fs.media.size() * sizeof(rtx::DMedium)) + 256;
+    size_t off_boxes = align(off_media + fs.media.size() * sizeof(rtx::DMedium));
+    size_t total = align(off_boxes + fs.world_boxes.size() * sizeof(float)) + 256;
     if (total > arena_bound) return bail(fail(RTX_ERR_NOMEM, "internal: arena larger than its bound"));
     uint8_t* host = c->h_stage + stage_used;
     std::memset(host, 0, total);
@@ -303,6 +316,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     put(off_perlins, fs.perlins.data(), fs.perlins.size() * sizeof(rtx::DPerlin));
     put(off_images, dimages.data(), dimages.size() * sizeof(rtx::DImage));
     put(off_media, fs.media.data(), fs.media.size() * sizeof(rtx::DMedium));
+    put(off_boxes, fs.world_boxes.data(), fs.world_boxes.size() * sizeof(float));
     if (c->device < kMaxDevices) {  // smallest cached arena that is large enough
         DeviceCache& dc = g_cache[c->device];
         std::lock_guard<std::mutex> lock(dc.m);
@@ -326,6 +340,26 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the staging buffer is reused by the next call
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(scene)"));
     uint8_t* base = (uint8_t*)s->d_arena;
+    if (fs.world_deferred) {
+        // the world BVH is built on the device, straight into the arena behind the host-built nodes
+        float lo[3], ext[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = 3.4e38f; ext[a] = -3.4e38f; }
+        for (int32_t k = 0; k < fs.world_count; ++k)
+            for (int a = 0; a < 3; ++a) {
+                float cc = 0.5f * (fs.world_boxes[(size_t)(6 * k + a)] + fs.world_boxes[(size_t)(6 * k + 3 + a)]);
+                lo[a] = std::fmin(lo[a], cc);
+                ext[a] = std::fmax(ext[a], cc);
+            }
+        for (int a = 0; a < 3; ++a) ext[a] -= lo[a];
+        int depth = 0;
+        e = rtx::lbvh_build(c->stream, fs.world_count, (const float*)(base + off_boxes), lo, ext, fs.world_first_record, (int32_t)host_nodes,
+                            (rtx::BvhNode*)(base + off_nodes) + host_nodes, &depth);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "lbvh_build"));
+        c->launches += 4;
+        if (1 + depth + 1 > rtx::kTraversalStack)
+            return bail(fail(RTX_ERR_UNSUPPORTED, "device-built BVH deeper than the traversal stack: use the host builder"));
+        fs.world_root = (int32_t)host_nodes;
+    }
     s->view.nodes = (const rtx::BvhNode*)(base + off_nodes);
     s->view.records = (const rtx::Record*)(base + off_records);
     s->view.xforms = (const rtx::XformOp*)(base + off_xforms);
@@ -338,7 +372,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->view.world_root = fs.world_root;
     s->view.n_media = fs.n_media;
     s->camera = fs.camera;
-    s->n_nodes = (int32_t)fs.nodes.size();
+    s->n_nodes = (int32_t)(host_nodes + lbvh_nodes);
     s->n_records = (int32_t)fs.records.size();
     s->n_xforms = (int32_t)fs.xforms.size();
     *out = s;

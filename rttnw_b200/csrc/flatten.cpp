@@ -279,6 +279,7 @@ struct Flattener {
     std::map<std::vector<int>, int32_t> chain_of_path;  // wrapper path (node indices) -> chain index
     int next_prim = 0, next_medium = 0;
     double t_a = 0, t_b = 1;  // time interval moving-sphere bounds must cover
+    bool defer_world = false;
 
     Flattener(const rtx_scene_desc& desc, FlatScene& o, std::string& e) : d(desc), out(o), err(e) {}
 
@@ -541,10 +542,26 @@ struct Flattener {
     }
 
     // Stack entries a traversal can need: the sentinel + one deferred sibling per level of the BVH.
-    int32_t build_world(World& w, Aabb& bounds) {
-        BvhBuilder b(out.nodes, out.records, w.items);
-        int32_t root = b.build(bounds);
-        out.max_stack = std::max(out.max_stack, 1 + b.depth + 1);
+    int32_t build_world(World& w, Aabb& bounds, bool defer = false) {
+        int32_t root = -1;
+        if (defer && w.items.size() >= 2) {
+            // the device builder (lbvh.cuh) makes this BVH: hand over the records in item order and their boxes
+            out.world_deferred = true;
+            out.world_first_record = (int32_t)out.records.size();
+            out.world_count = (int32_t)w.items.size();
+            out.world_boxes.reserve(6 * w.items.size());
+            bounds.reset();
+            for (const auto& it : w.items) {
+                out.records.push_back(it.rec);
+                for (int i = 0; i < 3; ++i) out.world_boxes.push_back(round_down(it.box.lo[i]));
+                for (int i = 0; i < 3; ++i) out.world_boxes.push_back(round_up(it.box.hi[i]));
+                bounds.grow(it.box);
+            }
+        } else {
+            BvhBuilder b(out.nodes, out.records, w.items);
+            root = b.build(bounds);
+            out.max_stack = std::max(out.max_stack, 1 + b.depth + 1);
+        }
         // media: records outside every BVH + a bounds list (only the main world has any)
         for (auto& m : w.media) {
             DMedium dm;
@@ -628,7 +645,7 @@ struct Flattener {
         std::vector<int> path;
         std::vector<XformOp> chain;
         if (!collect(d.root, path, chain, w, 0)) return false;
-        out.world_root = build_world(w, out.world_bounds);
+        out.world_root = build_world(w, out.world_bounds, defer_world);
         if (out.max_stack > kTraversalStack) return fail("BVH deeper than the device traversal stack");
         out.n_media = (int32_t)out.media.size();
         out.n_prims = next_prim;
@@ -639,9 +656,10 @@ struct Flattener {
 
 }  // namespace
 
-bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err) {
+bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err, bool defer_world_bvh) {
     out = FlatScene();
     Flattener f(desc, out, err);
+    f.defer_world = defer_world_bvh;
     return f.run();
 }
 

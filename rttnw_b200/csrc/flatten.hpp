@@ -30,6 +30,11 @@ struct FlatScene {
     std::vector<DPerlin> perlins;
     std::vector<DMedium> media;  // in medium-ordinal order
     int32_t max_stack = 0;       // traversal stack entries the deepest root-to-leaf path can need
+    // world BVH left to the device builder (lbvh.cuh): records [world_first_record, + world_count) are the world's
+    // items in item order, world_boxes holds their fp32 bounds (lo.xyz, hi.xyz; rounded outward), world_root is unset
+    bool world_deferred = false;
+    int32_t world_first_record = 0, world_count = 0;
+    std::vector<float> world_boxes;
     int32_t world_root = 0;
     int32_t n_media = 0;
     int32_t n_prims = 0;  // number of primitive ids handed out
@@ -38,7 +43,8 @@ struct FlatScene {
 };
 
 // Returns false and fills `err` on malformed input.
-bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err);
+// defer_world_bvh: leave the BVH over the world to the device builder when the world has at least two items.
+bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err, bool defer_world_bvh = false);
 
 // Structural invariants of the result (every record inside every ancestor box, every
 // record reachable exactly once per BVH, leaf sizes). Host logic test hook.
