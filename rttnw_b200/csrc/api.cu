@@ -68,7 +68,8 @@ struct rtx_ctx {
     int mode = 1;  // 1: wavefront (default), 0: megakernel (RTX_MODE=mega)
     // wavefront state, allocated at the first render
     void* d_pool = nullptr;
-    int pool_slots = 0, pool_slots_wanted = 1 << 19;  // 512 Ki slots x 108 B = 54 MB: stays in the 126 MB L2
+    int pool_slots = 0, pool_slots_wanted = 1 << 21;  // 2 Mi slots x 108 B = 226 MB. Measured on scene 9: 512 Ki 485 M samples/s,
+                                                      // 1 Mi 508 M, 2 Mi 516 M, 4 Mi 501 M (launch gaps and kernel tails vs L2 residency)
     unsigned long long* d_next_item = nullptr;
     unsigned int* d_active = nullptr;            // [2]
     unsigned long long* h_status = nullptr;      // pinned: [2][2] = {active, next_item} per batch parity
