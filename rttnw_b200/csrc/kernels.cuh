@@ -1084,7 +1084,7 @@ constexpr int kWfBlock = 128;   // trace kernel CTA; the pool size is a multiple
 #endif
 constexpr int kShadeBlock = WF_SHADE_BLOCK;  // shade kernel CTA (divides kWfBlock)
 #ifndef WF_TRACE_MINB
-#define WF_TRACE_MINB 8
+#define WF_TRACE_MINB 7
 #endif
 #ifndef WF_SHADE_MINB
 #define WF_SHADE_MINB 5
