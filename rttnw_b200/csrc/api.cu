@@ -503,7 +503,12 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                             unsigned long long* d_ray_count, bool counted) {
     const int64_t n_tiles = (int64_t)((p->width + rtx::kTileW - 1) / rtx::kTileW) * ((p->height + rtx::kTileH - 1) / rtx::kTileH);
     const unsigned long long total = (unsigned long long)n_tiles * 32ull * (unsigned long long)p->spp_count;
+    // pool size: the configured maximum, but a small job (few pool refills) is all ramp-up and drain with a pool
+    // that large: keep at least ~24 refills, down to 256 Ki slots
     int64_t slots = c->pool_slots_wanted;
+    if ((unsigned long long)slots > total / 24) slots = (int64_t)(total / 24);
+    if (slots < (256 << 10)) slots = 256 << 10;
+    if (slots > c->pool_slots_wanted) slots = c->pool_slots_wanted;
     if ((unsigned long long)slots > total) slots = (int64_t)total;
     slots = (slots + rtx::kWfBlock - 1) / rtx::kWfBlock * rtx::kWfBlock;  // whole CTAs
     int rc = wf_prepare(c, slots);

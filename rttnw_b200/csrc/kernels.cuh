@@ -13,6 +13,9 @@
 // hittable.rs:606-613,699-712 exactly as written, Q13/Q14), an iterative path loop with
 // per-lane path regeneration, and Philox4x32-10 counters for every random draw.
 #pragma once
+#ifndef SHADE_DENSE
+#define SHADE_DENSE 0  // 1: camera rays generated densely through shared memory (three passes per CTA, measured below)
+#endif
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -1090,7 +1093,10 @@ constexpr int kShadeBlock = WF_SHADE_BLOCK;  // shade kernel CTA (divides kWfBlo
 #define WF_SHADE_MINB 5
 #endif
 
-// Three passes per CTA so that each piece of code runs on full warps:
+// Default (SHADE_DENSE 0): one pass — shade the hit, refill emptied slots per warp (one dispenser atomic per
+// warp), medium pre-pass, write the slot. Alternative (SHADE_DENSE 1), measured A/B on one box at a 2 Mi-slot
+// pool: scene 9 525 vs 536 M samples/s, scene 2 1127 vs 1181, scene 3 1513 vs 1611, scene 7 596 vs 581 —
+// the barriers cost more than the dense generation saves except on the Cornell box. Its three passes:
 //   1. every thread shades the hit of its own slot (one level of color()); finished paths add their
 //      sample to the image and put the slot on a shared-memory list;
 //   2. the first ceil(Q / 32) warps generate the Q new camera rays densely (one dispenser atomic per
@@ -1104,17 +1110,21 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
     const int lane = tid & 31;
     const int i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < a.n_slots;
+#if SHADE_DENSE
     __shared__ int s_queue[kShadeBlock];
     __shared__ int s_count;
     __shared__ unsigned long long s_base;
     __shared__ double s_ray[7][kShadeBlock];
     __shared__ uint32_t s_pix[2][kShadeBlock];
     __shared__ unsigned char s_staged[kShadeBlock];
+#endif
     int32_t stack[kStackSize];  // only a ConstantMedium with a general boundary traverses here
     Tally<kCount> tally;
+#if SHADE_DENSE
     if (tid == 0) s_count = 0;
     s_staged[tid] = 0;
     __syncthreads();
+#endif
 
     // ---- pass 1: shade ----
     int bounce = valid ? a.pool.bounce[i] : -2;
@@ -1148,6 +1158,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
             fresh = true;
         }
     }
+#if SHADE_DENSE
     {   // empty slots (just emptied or empty before) queue up for a new path sample
         const bool want = bounce == -1;
         const unsigned m = __ballot_sync(FULL, want);
@@ -1197,6 +1208,38 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
         }
     }
 
+#else
+    {   // ---- refill empty slots per warp: consecutive items are the 32 pixels of one tile at one sample index ----
+        const bool want = bounce == -1;
+        unsigned m = __ballot_sync(FULL, want);
+        if (m != 0 && __ldcg(a.next_item) >= a.total_items) m = 0;  // dispenser already dry: no atomic
+        if (m != 0) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(a.next_item, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            const unsigned long long item = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+            if (want && item < a.total_items) {
+                const unsigned long long group = item >> 5;
+                const unsigned int tile = (unsigned int)(group / (unsigned long long)a.spp_count);
+                const unsigned int smp_i = (unsigned int)(group - (unsigned long long)tile * (unsigned long long)a.spp_count);
+                const int pi = (int)(item & 31ull);
+                const int px = (int)(tile % (unsigned int)a.tiles_x) * kTileW + (pi & (kTileW - 1));
+                const int row = (int)(tile / (unsigned int)a.tiles_x) * kTileH + (pi / kTileW);  // row 0 = top
+                if (px < a.width && row < a.height) {
+                    smp.pixel = (uint32_t)(row * a.width + px);
+                    smp.sample = (uint32_t)a.spp_begin + smp_i;
+                    smp.bounce = 0;
+                    camera_ray(a.cam, a.width, a.height, px, a.height - 1 - row, smp, ray);
+                    pc = PathColor{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+                    bounce = 0;
+                    fresh = true;
+                }
+            }
+        }
+    }
+
+#endif
     // ---- pass 3: the new ray: media first (their scatter point bounds the surface search), then out to the pool ----
     if (fresh) {
         smp.bounce = (uint32_t)bounce;
