@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -68,13 +69,19 @@ struct rtx_ctx {
     int mode = 1;  // 1: wavefront (default), 0: megakernel (RTX_MODE=mega)
     // wavefront state, allocated at the first render
     void* d_pool = nullptr;
-    int pool_slots = 0, pool_slots_wanted = 1 << 21;  // 2 Mi slots x 108 B = 226 MB. Measured on scene 9: 512 Ki 485 M samples/s,
-                                                      // 1 Mi 508 M, 2 Mi 516 M, 4 Mi 501 M (launch gaps and kernel tails vs L2 residency)
+    int pool_slots = 0, pool_slots_wanted = 1 << 19;  // 512 Ki slots x 108 B = 54 MB, in two partitions. Measured on scene 9 (M samples/s), one
+                                                      // stream: 512 Ki 485, 1 Mi 508, 2 Mi 516, 4 Mi 501; two streams: 256 Ki 511, 384 Ki 571,
+                                                      // 512 Ki 596, 768 Ki 590, 1 Mi 582, 2 Mi 567; three / four streams at 512 Ki: 593 / 585
     unsigned long long* d_next_item = nullptr;
     unsigned int* d_active = nullptr;            // [2]
-    unsigned long long* h_status = nullptr;      // pinned: [2][2] = {active, next_item} per batch parity
-    cudaEvent_t batch_done[2] = {nullptr, nullptr};
+    unsigned long long* h_status = nullptr;      // pinned: [partition][parity] x {active, next_item}
+    cudaEvent_t batch_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [partition][parity]
     int wf_batch = 8;
+    int wf_streams = 2;  // pool partitions driven concurrently on their own streams (RTX_WF_STREAMS, at most 4)
+    std::vector<cudaStream_t> aux_streams;
+    std::vector<cudaEvent_t> join_events;
+    cudaEvent_t fork_event = nullptr;
+    unsigned long long wf_iterations = 0;  // (shade, trace) iterations launched on partition 0
     unsigned long long launches = 0;  // kernels launched by this context (rtx_ctx_kernel_launches)
     int bvh_builder = 0;              // 0: host binned SAH (default), 1: device LBVH (rtx_ctx_set_bvh_builder, RTX_BVH=lbvh)
     uint8_t* h_stage = nullptr;       // pinned staging buffer of rtx_scene_create (every H2D copy leaves from here)
@@ -144,6 +151,7 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->node_burst = env_int("RTX_NODE_BURST", c->node_burst);
     c->pool_slots_wanted = env_int("RTX_WF_SLOTS", c->pool_slots_wanted);
     c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
+    c->wf_streams = std::min(4, env_int("RTX_WF_STREAMS", c->wf_streams));
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
     if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : 0;
     // the traversal stack lives in local memory: prefer L1 over shared for it
@@ -167,6 +175,9 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     for (auto& e : c->batch_done)
         if (e) cudaEventDestroy(e);
     for (auto e : c->prof_events) cudaEventDestroy(e);
+    for (auto e : c->join_events) cudaEventDestroy(e);
+    for (auto st : c->aux_streams) cudaStreamDestroy(st);
+    if (c->fork_event) cudaEventDestroy(c->fork_event);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTX_OK;
@@ -485,9 +496,18 @@ static int wf_prepare(rtx_ctx* c, int64_t slots) {
         c->pool_slots = (int)slots;
     }
     if (!c->d_next_item) CU(cudaMalloc(&c->d_next_item, sizeof(unsigned long long)));
-    if (!c->d_active) CU(cudaMalloc(&c->d_active, 2 * sizeof(unsigned int)));
+    if (!c->d_active) CU(cudaMalloc(&c->d_active, 8 * sizeof(unsigned int)));
 
-    if (!c->h_status) CU(cudaMallocHost(&c->h_status, 4 * sizeof(unsigned long long)));
+    if (!c->h_status) CU(cudaMallocHost(&c->h_status, 16 * sizeof(unsigned long long)));
+    while ((int)c->aux_streams.size() < c->wf_streams - 1) {
+        cudaStream_t st;
+        cudaEvent_t ev;
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->aux_streams.push_back(st);
+        c->join_events.push_back(ev);
+    }
+    if (!c->fork_event) CU(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
     for (auto& e : c->batch_done)
         if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return RTX_OK;
@@ -540,12 +560,44 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     CU(cudaMemsetAsync(a.pool.bounce, 0xFF, (size_t)slots * 4, c->stream));  // every slot empty (-1)
     CU(cudaMemsetAsync(c->d_next_item, 0, sizeof(unsigned long long), c->stream));
     float4* acc = reinterpret_cast<float4*>(d_accum);
-    const unsigned grid = (unsigned)((slots + rtx::kWfBlock - 1) / rtx::kWfBlock);
-    const unsigned sgrid = (unsigned)(slots / rtx::kShadeBlock);
     const int batch = c->wf_batch;
+    // P partitions of the pool, each driven on its own stream: the shade kernel of one partition (latency bound,
+    // streams the pool) can share the SMs with the trace kernel of another (issue bound). Partition 0 runs on the
+    // ctx stream; the others fork from it here and join it at the end.
+    const int P = (slots >= (int64_t)c->wf_streams * 4 * rtx::kWfBlock) ? c->wf_streams : 1;
+    struct Part {
+        rtx::WfArgs a;
+        cudaStream_t stream;
+        unsigned grid, sgrid;
+        bool done;
+    };
+    std::vector<Part> parts((size_t)P);
+    {
+        int64_t per = slots / P / rtx::kWfBlock * rtx::kWfBlock;
+        for (int q = 0; q < P; ++q) {
+            Part& pt = parts[(size_t)q];
+            int64_t begin = (int64_t)q * per, count = q == P - 1 ? slots - begin : per;
+            pt.a = a;
+            pt.a.n_slots = (int32_t)count;
+            double** d8[8] = {&pt.a.pool.ox, &pt.a.pool.oy, &pt.a.pool.oz, &pt.a.pool.dx, &pt.a.pool.dy, &pt.a.pool.dz, &pt.a.pool.time, &pt.a.pool.best_t};
+            for (auto pp : d8) *pp += begin;
+            pt.a.pool.best_rec += begin; pt.a.pool.best_chain += begin; pt.a.pool.bounce += begin;
+            pt.a.pool.pixel += begin; pt.a.pool.sample += begin;
+            float** f4[6] = {&pt.a.pool.thr_r, &pt.a.pool.thr_g, &pt.a.pool.thr_b, &pt.a.pool.rad_r, &pt.a.pool.rad_g, &pt.a.pool.rad_b};
+            for (auto pp : f4) *pp += begin;
+            pt.grid = (unsigned)((count + rtx::kWfBlock - 1) / rtx::kWfBlock);
+            pt.sgrid = (unsigned)(count / rtx::kShadeBlock);
+            pt.done = false;
+            pt.stream = q == 0 ? c->stream : c->aux_streams[(size_t)q - 1];
+        }
+        if (P > 1) {
+            CU(cudaEventRecord(c->fork_event, c->stream));
+            for (int q = 1; q < P; ++q) CU(cudaStreamWaitEvent(parts[(size_t)q].stream, c->fork_event, 0));
+        }
+    }
     size_t prof_used = 0;
-    // every kProfStride-th iteration is bracketed (events between back-to-back launches cost ~10 % when every
-    // launch has them); the accumulated times are scaled back up by the stride
+    // every kProfStride-th iteration of partition 0 is bracketed (events between back-to-back launches cost ~10 %
+    // when every launch has them); the accumulated times are scaled back up by the stride
     constexpr int kProfStride = 8;
     long long iteration = 0;
     bool prof_now = false;
@@ -559,42 +611,60 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
         }
         return cudaEventRecord(c->prof_events[prof_used++], c->stream);
     };
-    for (int k = 0;; ++k) {
+    int remaining = P;
+    for (int k = 0; remaining > 0; ++k) {
         const int par = k & 1;
-        for (int it = 0; it < batch; ++it) {
-            unsigned int* active = nullptr;
-            if (it == batch - 1) {
-                active = c->d_active + par;
-                CU(cudaMemsetAsync(active, 0, sizeof(unsigned int), c->stream));
+        for (int q = 0; q < P; ++q) {
+            Part& pt = parts[(size_t)q];
+            if (pt.done) continue;
+            unsigned int* d_act = c->d_active + 2 * q + par;
+            for (int it = 0; it < batch; ++it) {
+                unsigned int* active = nullptr;
+                if (it == batch - 1) {
+                    active = d_act;
+                    CU(cudaMemsetAsync(active, 0, sizeof(unsigned int), pt.stream));
+                }
+                prof_now = q == 0 && c->profiling && (iteration++ % kProfStride) == 0;
+                CU(prof_mark());
+                if (counted) {
+                    rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                    CU(prof_mark());
+                    CU(prof_mark());
+                    rtx::wf_trace_kernel<true><<<pt.grid, rtx::kWfBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
+                } else {
+                    rtx::wf_shade_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
+                    CU(prof_mark());
+                    CU(prof_mark());
+                    rtx::wf_trace_kernel<false><<<pt.grid, rtx::kWfBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
+                }
+                CU(prof_mark());
             }
-            prof_now = c->profiling && (iteration++ % kProfStride) == 0;
-            CU(prof_mark());
-            if (counted) {
-                rtx::wf_shade_kernel<true><<<sgrid, rtx::kShadeBlock, 0, c->stream>>>(a, acc, active, c->d_counters);
-                CU(prof_mark());
-                CU(prof_mark());
-                rtx::wf_trace_kernel<true><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, c->d_counters);
-            } else {
-                rtx::wf_shade_kernel<false><<<sgrid, rtx::kShadeBlock, 0, c->stream>>>(a, acc, active, nullptr);
-                CU(prof_mark());
-                CU(prof_mark());
-                rtx::wf_trace_kernel<false><<<grid, rtx::kWfBlock, 0, c->stream>>>(a.sc, a.pool, a.n_slots, d_ray_count, nullptr);
-            }
-            CU(prof_mark());
+            CU(cudaGetLastError());
+            c->launches += 2ull * (unsigned long long)batch;
+            if (q == 0) c->wf_iterations += (unsigned long long)batch;
+            // status of this batch -> pinned memory (active is 32-bit: widen on the host side)
+            unsigned long long* hs = c->h_status + 4 * q + 2 * par;
+            hs[0] = 0;
+            CU(cudaMemcpyAsync(&hs[0], d_act, sizeof(unsigned int), cudaMemcpyDeviceToHost, pt.stream));
+            CU(cudaMemcpyAsync(&hs[1], c->d_next_item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, pt.stream));
+            CU(cudaEventRecord(c->batch_done[2 * q + par], pt.stream));
         }
-        CU(cudaGetLastError());
-        c->launches += 2ull * (unsigned long long)batch;
-        // status of this batch -> pinned memory (active is 32-bit: widen on the host side)
-        c->h_status[2 * par] = 0;
-        CU(cudaMemcpyAsync(&c->h_status[2 * par], c->d_active + par, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(&c->h_status[2 * par + 1], c->d_next_item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaEventRecord(c->batch_done[par], c->stream));
-        if (k >= 1) {  // look at the previous batch while this one runs
+        if (k >= 1) {  // look at the previous batches while these run
             const int prev = par ^ 1;
-            CU(cudaEventSynchronize(c->batch_done[prev]));
-            if ((unsigned int)c->h_status[2 * prev] == 0 && c->h_status[2 * prev + 1] >= total) break;
+            for (int q = 0; q < P; ++q) {
+                Part& pt = parts[(size_t)q];
+                if (pt.done) continue;
+                CU(cudaEventSynchronize(c->batch_done[2 * q + prev]));
+                const unsigned long long* hs = c->h_status + 4 * q + 2 * prev;
+                if ((unsigned int)hs[0] == 0 && hs[1] >= total) { pt.done = true; --remaining; }
+            }
         }
     }
+    if (P > 1)
+        for (int q = 1; q < P; ++q) {
+            CU(cudaEventRecord(c->join_events[(size_t)q - 1], parts[(size_t)q].stream));
+            CU(cudaStreamWaitEvent(c->stream, c->join_events[(size_t)q - 1], 0));
+        }
     // the batch queued behind the one that ended dry runs over empty slots only; later calls on this
     // stream are ordered after it
     if (c->profiling && prof_used >= 4) {
