@@ -424,12 +424,21 @@ __device__ __forceinline__ void media_prepass(const SceneView& sc, const RayD& r
 struct HitOut {
     d3 p, n;       // point and (face-flipped, possibly Q14-mangled) normal
     d3 on;         // outward unit normal in object space (spheres: the argument of Sphere::uv)
-    double u, v;   // rectangles always; spheres when kPrecise
+    double u, v;   // when kPrecise; the render path computes them only for textures that look at them
+    double ru, rv; // rectangles, render path: the in-plane coordinates (p0, p1) of the hit, for rect_uv()
     int32_t material;  // material index, or -(1 + texture) for a medium's Isotropic
     int32_t prim_id;
     int32_t type;
     bool front_face;
 };
+
+// Rectangle u, v (hittable.rs:515-516) from the in-plane hit coordinates finalize_hit<false> left in ru, rv
+__device__ __forceinline__ void rect_uv(const SceneView& sc, int32_t rec, double p0, double p1, float& u, float& v) {
+    const double* d = sc.records[rec].d;
+    double r0 = ldg_d(d), r1 = ldg_d(d + 1), r2 = ldg_d(d + 2), r3 = ldg_d(d + 3);
+    u = (float)((p0 - r0) / (r1 - r0));
+    v = (float)((p1 - r2) / (r3 - r2));
+}
 
 __device__ __forceinline__ void sphere_uv(d3 p, double& u, double& v) {  // hittable.rs:77-83
     const double PI = 3.14159265358979323846;
@@ -459,6 +468,8 @@ __device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ra
     bool ff;
     out.u = 0.0;
     out.v = 0.0;
+    out.ru = 0.0;
+    out.rv = 0.0;
     out.type = h.x;
     out.prim_id = h.z;
     out.material = h.y;
@@ -489,8 +500,13 @@ __device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ra
             int a0 = plane == 2 ? 1 : 0, a1 = plane == 0 ? 1 : 2;
             double r0 = ldg_d(d), r1 = ldg_d(d + 1), r2 = ldg_d(d + 2), r3 = ldg_d(d + 3);
             double p0 = comp(o, a0) + t * comp(dir, a0), p1 = comp(o, a1) + t * comp(dir, a1);
-            out.u = (p0 - r0) / (r1 - r0);  // hittable.rs:515-516
-            out.v = (p1 - r2) / (r3 - r2);
+            if (kPrecise) {
+                out.u = (p0 - r0) / (r1 - r0);  // hittable.rs:515-516
+                out.v = (p1 - r2) / (r3 - r2);
+            } else {  // two f64 divisions only an ImageTexture would look at: left to rect_uv()
+                out.ru = p0;
+                out.rv = p1;
+            }
             outward = mk(plane == 2 ? 1.0 : 0.0, plane == 1 ? 1.0 : 0.0, plane == 0 ? 1.0 : 0.0);  // +k axis (Q11)
         }
         out.on = outward;
@@ -722,12 +738,15 @@ __device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __re
         }
         // Texture::value for the three materials that carry one (material.rs:97,247,262)
         if (mkind == RTX_MAT_LAMBERTIAN || mkind == RTX_MAT_ISOTROPIC || mkind == RTX_MAT_DIFFUSE_LIGHT) {
-            float tu = (float)ho.u, tv = (float)ho.v;
-            if (ho.type == REC_SPHERE && sc.textures[mtex]._pad) {
-                // Sphere::uv (hittable.rs:77-83) in fp32: only needed for image lookups
-                const float PI = 3.14159265358979f;
-                tv = acosf(-(float)ho.on.y) / PI;
-                tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+            float tu = 0.f, tv = 0.f;  // (moving spheres and media: u = v = 0, Q10 / Q16)
+            if (sc.textures[mtex]._pad) {  // only image lookups need the surface coordinates
+                if (ho.type == REC_SPHERE) {  // Sphere::uv (hittable.rs:77-83) in fp32
+                    const float PI = 3.14159265358979f;
+                    tv = acosf(-(float)ho.on.y) / PI;
+                    tu = (atan2f(-(float)ho.on.z, (float)ho.on.x) + PI) / (2.f * PI);
+                } else if (ho.type >= REC_RECT_XY && ho.type <= REC_RECT_YZ) {
+                    rect_uv(sc, best.rec, ho.ru, ho.rv, tu, tv);
+                }
             }
             DTexture t = resolve_texture(sc, mtex, ho.p);
             if (kDeferNoise && t.kind == RTX_TEX_NOISE) {

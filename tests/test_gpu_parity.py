@@ -478,3 +478,24 @@ def test_device_built_bvh_random_trees_and_render():
         assert np.isclose(got, ref, rtol=2e-3, atol=2e-3).all(axis=2).mean() > 0.97
     finally:
         c.close()
+
+
+def test_image_texture_on_rectangles_and_boxes(ctx, earth_rgba):
+    """Rectangle u, v (hittable.rs:515-516) reach an ImageTexture — also on the faces of a wrapped Cube, whose
+    hit record comes from the face's rectangle record — and an image-emitting light. Same counters as the oracle."""
+    img = S.ImageTexture(earth_rgba[::8, ::8].copy())
+    cam = S.CameraDescriptor(lookfrom=(0, 3, -9), lookat=(0, 1, 0), vertical_fov=50.0)
+    world = S.List([
+        S.XZ.rectangle(S.Lambertian(img), (-6, 6), (-6, 6), 0.0),
+        S.XY.rectangle(S.DiffuseLight(img), (-3, 3), (0.5, 3.5), 4.0),
+        S.Cube((-1, 0, -1), (1, 2, 1), S.Lambertian(img)).rotate_y(30.0).translate((1.5, 0.0, 0.5)),
+        S.YZ.rectangle(S.Lambertian(S.CheckerTexture(img, (0.2, 0.3, 0.9))), (0, 3), (-3, 3), -4.0),
+    ])
+    desc = S.Scene(world, cam, (0.05, 0.05, 0.05)).to_desc()
+    gsc, osc = both(ctx, desc)
+    for depth in (1, 2):
+        got = gpu_sum(gsc, 64, 48, 4, seed=5, max_depth=depth).cpu().numpy()[..., :3]
+        ref, _ = osc.render_sum(64, 48, 4, seed=5, max_depth=depth)
+        close = np.isclose(got, ref, rtol=2e-3, atol=2e-3).all(axis=2)
+        assert close.mean() > 0.97, (depth, close.mean())
+    assert got.std() > 0.01  # the texture is really there
