@@ -499,3 +499,51 @@ def test_image_texture_on_rectangles_and_boxes(ctx, earth_rgba):
         close = np.isclose(got, ref, rtol=2e-3, atol=2e-3).all(axis=2)
         assert close.mean() > 0.97, (depth, close.mean())
     assert got.std() > 0.01  # the texture is really there
+
+
+def test_full_size_final_scene_properties(ctx, earth_rgba):
+    """BASELINE.json's frame (scene 9, 800x800) at a spp the GPU renders in a blink, checked through
+    size-independent properties: every pixel got exactly its samples, nothing is NaN / negative, splitting the
+    samples over two calls changes nothing but the summation order, and the frame's mean colour agrees with the
+    oracle's render of a 10x smaller frame of the same camera (a different, much sparser set of paths)."""
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(9))
+    w = h = 800
+    spp = 64
+    one = gpu_sum(gsc, w, h, spp, seed=21).cpu().numpy()
+    two = gpu_sum(gsc, w, h, spp, seed=21, chunk=24).cpu().numpy()
+    assert np.array_equal(one[..., 3], np.full((h, w), float(spp), dtype=np.float32))
+    assert np.isfinite(one).all() and (one[..., :3] >= 0).all()
+    assert np.allclose(one, two, rtol=2e-5, atol=2e-4)
+    osc = O.OracleScene.builtin(9, earth=earth_rgba)
+    ref, _ = osc.render_sum(80, 80, 256, seed=22)
+    mean_gpu = one[..., :3].reshape(-1, 3).mean(axis=0) / spp
+    mean_ref = ref.reshape(-1, 3).mean(axis=0) / 256
+    assert np.allclose(mean_gpu, mean_ref, rtol=0.03), (mean_gpu, mean_ref)
+    rgba = gsc.tonemap(gsc.new_accum(w, h) + torch_from(one, ctx))
+    assert rgba.shape == (h, w, 4) and rgba[..., 3].min() == 255
+
+
+def torch_from(arr, ctx):
+    import torch
+    return torch.from_numpy(arr).to(f"cuda:{ctx.device}")
+
+
+def test_bad_arguments_are_refused(ctx):
+    import ctypes as C
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(2))
+    acc = gsc.new_accum(8, 8)
+    lib = ctx.lib
+    for bad in (abi.RenderParams(0, 8, 0, 1, 50, 0, 1), abi.RenderParams(8, 8, -1, 1, 50, 0, 1), abi.RenderParams(8, 8, 0, -1, 50, 0, 1),
+                abi.RenderParams(8, 8, 0, 1, -1, 0, 1), abi.RenderParams(8, 8, 0, (1 << 26) + 1, 50, 0, 1)):
+        assert lib.rtx_render(ctx.h, gsc.h, C.byref(bad), acc.data_ptr(), None) == -1
+    assert lib.rtx_render(ctx.h, gsc.h, None, acc.data_ptr(), None) == -1
+    assert lib.rtx_trace_rays(ctx.h, gsc.h, -1, None, None) == -1
+    assert lib.rtx_ctx_set_bvh_builder(ctx.h, 7) == -1
+    # zero samples and depth 0 are valid requests: nothing traced, counts move by spp
+    gsc.render_into(acc, 0, 0)
+    assert float(acc.sum()) == 0.0
+    gsc.render_into(acc, 0, 5, max_depth=0)
+    a = acc.cpu().numpy()
+    assert (a[..., 3] == 5).all() and (a[..., :3] == 0).all()
+    h = C.c_void_p()
+    assert lib.rtx_ctx_create(99, None, C.byref(h)) == -1 and b"no such CUDA device" in lib.rtx_last_error()
