@@ -547,3 +547,38 @@ def test_bad_arguments_are_refused(ctx):
     assert (a[..., 3] == 5).all() and (a[..., :3] == 0).all()
     h = C.c_void_p()
     assert lib.rtx_ctx_create(99, None, C.byref(h)) == -1 and b"no such CUDA device" in lib.rtx_last_error()
+
+
+def test_final_scene_matches_the_reference_shipped_image(ctx):
+    """The reference's own 800x800 render of the final scene (image.png, ~10k spp; committed 8x8
+    box-filtered as tests/golden/final_ref_100.npy) against this backend's render of scene 9. The ground
+    boxes and the sphere cluster are drawn from an unseeded RNG in the reference, so the lower third of
+    the frame only agrees in the mean; everything else — camera, fog, light, glass, metal, earth and
+    marble spheres, gamma — is deterministic and agrees block by block."""
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "final_ref_100.npy")).astype(np.float64)
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(9))
+    acc = gpu_sum(gsc, 800, 800, 4096, seed=4, chunk=512)  # (sqrt gamma per pixel biases dark regions low at small spp)
+    rgb = gsc.tonemap(acc)[..., :3].astype(np.float64)
+    ours = rgb.reshape(100, 8, 100, 8, 3).mean(axis=(1, 3))
+    diff = ours - ref
+    assert np.abs(diff.mean(axis=(0, 1))).max() < 1.5, diff.mean(axis=(0, 1))  # whole-frame mean colour, 8-bit units
+    blocks = np.abs(diff.reshape(10, 10, 10, 10, 3).mean(axis=(1, 3))).mean(axis=2)  # 80x80-pixel regions
+    upper = blocks[:5]  # no random geometry above the horizon of the ground boxes
+    assert np.median(upper) < 0.8 and upper.max() < 7.0, np.round(blocks, 1)
+    assert np.corrcoef(ours.mean(axis=2).ravel(), ref.mean(axis=2).ravel())[0, 1] > 0.85
+
+
+def test_cornell_box_matches_the_reference_shipped_image(ctx):
+    """cornel_box.png (the reference's render of its deterministic Cornell box, 600x600 at ~200 spp; committed
+    8x8 box-filtered) against this backend's render at the same size and spp — same sqrt-gamma bias, so the
+    comparison is region by region in 8-bit units, including the nearly black rotated-box faces that only
+    YRotate's sequential-update behaviour (hittable.rs:700-705, Q14) produces."""
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_ref_75.npy")).astype(np.float64)
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(7))
+    rgb = gsc.tonemap(gpu_sum(gsc, 600, 600, 200, seed=8))[..., :3].astype(np.float64)
+    ours = rgb.reshape(75, 8, 75, 8, 3).mean(axis=(1, 3))
+    diff = ours - ref
+    assert abs(diff.mean()) < 1.0
+    blocks = diff.reshape(15, 5, 15, 5, 3).mean(axis=(1, 3))
+    assert np.abs(blocks).max() < 14.0 and np.sqrt((blocks ** 2).mean()) < 4.0, np.round(np.abs(blocks).mean(axis=2), 1)
+    assert ours[37:55, 27:33].mean() < 25.0 and ours[12:15, 32:42].mean() > 120.0  # dark side faces, bright top
