@@ -1,0 +1,7 @@
+// Links librttnw_b200.so (built by `make all` at the repository root).
+fn main() {
+    let dir = std::env::var("RTTNW_B200_LIB_DIR").unwrap_or_else(|_| "../../rttnw_b200/lib".to_string());
+    println!("cargo:rustc-link-search=native={}", dir);
+    println!("cargo:rustc-link-lib=dylib=rttnw_b200");
+    println!("cargo:rerun-if-env-changed=RTTNW_B200_LIB_DIR");
+}
