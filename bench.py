@@ -129,7 +129,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "rays_per_sec": total_rays / total_t,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -194,8 +194,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG >= VERSION) to stdout; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d, w, h = workload(args)
     lib = abi.load()
@@ -428,12 +426,34 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line. Libraries write banners to file descriptor 1 (NCCL prints its version
+    there at NCCL_DEBUG >= VERSION): point fd 1 at stderr for the rest of the run and keep the real one for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse()
     if args.impl == "reference":
+        claim_stdout()
         run_reference(args)
         return
     if args.gpus > 1 and "RANK" not in os.environ:
@@ -441,6 +461,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     run_ours(args)
 
 
