@@ -585,7 +585,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             pt.a.pool.pixel += begin; pt.a.pool.sample += begin;
             float** f4[6] = {&pt.a.pool.thr_r, &pt.a.pool.thr_g, &pt.a.pool.thr_b, &pt.a.pool.rad_r, &pt.a.pool.rad_g, &pt.a.pool.rad_b};
             for (auto pp : f4) *pp += begin;
-            pt.grid = (unsigned)((count + rtx::kWfBlock - 1) / rtx::kWfBlock);
+            pt.grid = (unsigned)(count / rtx::kTraceBlock);
             pt.sgrid = (unsigned)(count / rtx::kShadeBlock);
             pt.done = false;
             pt.stream = q == 0 ? c->stream : c->aux_streams[(size_t)q - 1];
@@ -630,12 +630,12 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                     rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
                     CU(prof_mark());
                     CU(prof_mark());
-                    rtx::wf_trace_kernel<true><<<pt.grid, rtx::kWfBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
+                    rtx::wf_trace_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
                 } else {
                     rtx::wf_shade_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
                     CU(prof_mark());
                     CU(prof_mark());
-                    rtx::wf_trace_kernel<false><<<pt.grid, rtx::kWfBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
+                    rtx::wf_trace_kernel<false><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
                 }
                 CU(prof_mark());
             }

@@ -1105,6 +1105,10 @@ constexpr int kWfBlock = 128;   // trace kernel CTA; the pool size is a multiple
 #define WF_SHADE_BLOCK 128
 #endif
 constexpr int kShadeBlock = WF_SHADE_BLOCK;  // shade kernel CTA (divides kWfBlock)
+#ifndef WF_TRACE_BLOCK
+#define WF_TRACE_BLOCK 128
+#endif
+constexpr int kTraceBlock = WF_TRACE_BLOCK;  // trace kernel CTA (divides kWfBlock): registers are released per CTA
 #ifndef WF_TRACE_MINB
 #define WF_TRACE_MINB 7
 #endif
@@ -1290,7 +1294,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
 }
 
 template <bool kCount>
-__global__ void __launch_bounds__(kWfBlock, WF_TRACE_MINB) wf_trace_kernel(SceneView sc, PathPool pool, int n_slots, unsigned long long* ray_count,
+__global__ void __launch_bounds__(kTraceBlock, WF_TRACE_MINB * (128 / kTraceBlock)) wf_trace_kernel(SceneView sc, PathPool pool, int n_slots, unsigned long long* ray_count,
                                                             Counters* counters) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
