@@ -13,6 +13,9 @@
 // hittable.rs:606-613,699-712 exactly as written, Q13/Q14), an iterative path loop with
 // per-lane path regeneration, and Philox4x32-10 counters for every random draw.
 #pragma once
+#ifndef K1_MINB
+#define K1_MINB 5  // 96 registers: 4.8 / 4.3 / 4.2 Grays/s on primary / secondary / tertiary rays of scene 9 (4, 6, 7 CTAs per SM: 4.3, 4.3, 4.5 on primaries)
+#endif
 #ifndef SHADE_DENSE
 #define SHADE_DENSE 0  // 1: camera rays generated densely through shared memory (three passes per CTA, measured below)
 #endif
@@ -541,7 +544,7 @@ __device__ __forceinline__ void finalize_hit(const SceneView& sc, const RayD& ra
 // K1: fixed rays
 // ---------------------------------------------------------------------------
 template <bool kCount>
-__global__ void __launch_bounds__(128) trace_rays_kernel(SceneView sc, int64_t n, const rtx_ray* __restrict__ rays,
+__global__ void __launch_bounds__(128, K1_MINB) trace_rays_kernel(SceneView sc, int64_t n, const rtx_ray* __restrict__ rays,
                                                          rtx_hit* __restrict__ hits, Counters* counters) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Tally<kCount> tally;
