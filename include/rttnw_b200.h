@@ -195,7 +195,7 @@ typedef struct rtx_trace_stats {
     double node_visits;    /* 64-byte inner nodes fetched                      */
     double sphere_tests;   /* Sphere + MovingSphere intersection evaluations   */
     double rect_tests;
-    double instance_enters;
+    double instance_enters; /* always 0 since wrapped primitives carry their own transform chain */
     double medium_tests;
 } rtx_trace_stats;
 

@@ -36,7 +36,7 @@ enum RecType : int32_t {
                        // Medium records are not BVH leaves: they are listed in SceneView::media.
 };
 
-// One 96-byte record per leaf primitive / instance / medium. Geometry is f64: the reference
+// One 96-byte record per leaf primitive / box face / medium. Geometry is f64: the reference
 // computes in f64 (vec3.rs:12) and the fixed-ray contract (t, normal, u, v within 1e-5 on
 // radius-1000 and radius-5000 spheres) cannot be met by an fp32 quadratic.
 struct alignas(16) Record {

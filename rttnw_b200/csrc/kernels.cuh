@@ -1,17 +1,19 @@
 // kernels.cuh — device code of the rttnw hot path for sm_100a.
 //
-//   K1 trace_rays_kernel : every Hittable::hit + Bound::hit of src/math/hittable.rs / bound.rs
-//   K2 render_kernel     : render()'s pixel loop + color() + Material::scatter/emitted +
-//                          Texture::value (src/main.rs:26-45,202-217, material.rs, texture.rs, noise.rs)
-//   K3 tonemap_kernel    : mean / sqrt / clamp / quantise (src/main.rs:217-225)
-//      reduce_tonemap_peers_kernel : K3 fused with the multi-GPU sum over NVLink peer pointers
+//   K1  trace_rays_kernel : every Hittable::hit + Bound::hit of src/math/hittable.rs / bound.rs
+//   K2a wf_shade_kernel   : render()'s pixel loop + one level of color() + Material::scatter/emitted +
+//                           Texture::value (src/main.rs:26-45,202-217, material.rs, texture.rs, noise.rs)
+//   K2b wf_trace_kernel   : the closest surface hit of every ray in flight (the wavefront's other half)
+//       render_kernel     : the same path loop as ONE kernel (megakernel; kept for the comparison in DESIGN.md)
+//   K3  tonemap_kernel    : mean / sqrt / clamp / quantise (src/main.rs:217-225)
+//       reduce_tonemap_peers_kernel : K3 fused with the multi-GPU sum over NVLink peer pointers
 //
 // The reference recurses through trait objects in f64. Here: an iterative while-while BVH
-// traversal (fp32 conservative slab tests on 64-byte nodes, exact-form f64 primitive tests on
-// 96-byte records), instances entered by switching the ray's space inside the same loop,
-// hit records finalised once per query (including the Translate/YRotate post-processing of
-// hittable.rs:606-613,699-712 exactly as written, Q13/Q14), an iterative path loop with
-// per-lane path regeneration, and Philox4x32-10 counters for every random draw.
+// traversal in world space (fp32 conservative slab tests on 64-byte nodes, exact-form f64
+// primitive tests on 96-byte records; a primitive under Translate / YRotate wrappers pushes the
+// ray through its composed transform chain first), hit records finalised once per query
+// (including the Translate/YRotate post-processing of hittable.rs:606-613,699-712 exactly as
+// written, Q13/Q14), an iterative path loop and Philox4x32-10 counters for every random draw.
 #pragma once
 #ifndef K1_MINB
 #define K1_MINB 5  // 96 registers: 4.8 / 4.3 / 4.2 Grays/s on primary / secondary / tertiary rays of scene 9 (4, 6, 7 CTAs per SM: 4.3, 4.3, 4.5 on primaries)
@@ -104,8 +106,8 @@ struct Tally<true> {
 
 // ---------------------------------------------------------------------------
 // The fp32 half of a ray in the space currently being traversed: directed-rounding slab
-// parameters for the BVH boxes. The f64 half (origin, direction) is the ray itself, or the ray
-// pushed through the instance's transform chain when a leaf inside an instance is tested.
+// parameters for the BVH boxes (world space). The f64 half (origin, direction) is the ray itself,
+// pushed through a primitive's transform chain when that primitive is tested (test_geometry).
 // ---------------------------------------------------------------------------
 struct SlabRay {
     float idx, idy, idz;     // fp32 1/d, magnitude clamped to 2^100
@@ -206,7 +208,7 @@ __device__ __forceinline__ bool rect_hit(d3 o, d3 d, int plane, const double* r,
 struct Best {
     double t;       // closest accepted distance so far (the `closest` of List::hit, hittable.rs:155)
     int32_t rec;    // record index, -1 = none
-    int32_t chain;  // transform chain of the instance the record was hit in (index into SceneView::chains)
+    int32_t chain;  // transform chain of the record that was hit (index into SceneView::chains; 0 = none)
 };
 
 constexpr int kStackSize = kTraversalStack;
@@ -881,7 +883,7 @@ enum LaneState : int32_t {
 // takes the next (pixel, sample) item from the warp's pool (an 8x4 pixel tile x spp_count
 // samples, refilled from a global tile counter), so no lane waits for a neighbour's longer
 // path. The work of a path step comes in three kinds with very different code — BVH node steps
-// (fp32), leaf events (f64 primitive tests, entering / leaving an instance) and shading (hit
+// (fp32), leaf events (f64 primitive tests) and shading (hit
 // record, material, texture, Philox, next ray, medium pre-pass) — and lanes reach them at
 // different times. Instead of letting every lane run its own branch (the first version of this
 // kernel: 7 of 32 lanes active on average), the warp votes each iteration and runs ONE phase for
