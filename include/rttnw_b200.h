@@ -242,6 +242,10 @@ int rtx_ctx_kernel_launches(rtx_ctx* ctx, unsigned long long* out);
 int rtx_ctx_set_profiling(rtx_ctx* ctx, int on);
 int rtx_ctx_profile_read(rtx_ctx* ctx, double* shade_ms, double* trace_ms,
                          unsigned long long* iterations, int reset);
+/* Roofline denominator for this path (benchmark bookkeeping): the flattened scene and the path pool live in L2,
+ * so the bandwidth that bounds BVH-node traffic is L2's, not HBM's. Reads an L2-resident buffer of `bytes`
+ * (0 = 32 MiB) `repeats` times (0 = 64) with 16-byte loads that skip L1 from every SM and reports GB/s. */
+int rtx_ctx_measure_l2_read(rtx_ctx* ctx, unsigned long long bytes, int repeats, double* gbytes_per_s);
 
 /* ---- scene: flattens the tree, builds the BVHs, uploads (host memory is
  * copied; the caller keeps ownership of everything in `desc`). ---- */

@@ -114,6 +114,7 @@ SIGNATURES = {
     "rtx_ctx_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rtx_ctx_set_profiling": (C.c_int, [_P, C.c_int]),
     "rtx_ctx_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
+    "rtx_ctx_measure_l2_read": (C.c_int, [_P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "rtx_scene_create": (C.c_int, [_P, C.POINTER(SceneDesc), C.POINTER(_P)]),
     "rtx_scene_destroy": (C.c_int, [_P]),
     "rtx_scene_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),

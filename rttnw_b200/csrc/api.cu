@@ -203,6 +203,47 @@ int rtx_ctx_profile_read(rtx_ctx* c, double* shade_ms, double* trace_ms, unsigne
     if (reset) { c->prof_shade_ms = c->prof_trace_ms = 0; c->prof_iterations = 0; }
     return RTX_OK;
 }
+int rtx_ctx_measure_l2_read(rtx_ctx* c, unsigned long long bytes, int repeats, double* gbytes_per_s) {
+    if (!c || !gbytes_per_s) return fail(RTX_ERR_INVALID, "NULL argument");
+    if (bytes == 0) bytes = 32ull << 20;
+    if (repeats <= 0) repeats = 64;
+    if (bytes < (1ull << 20) || bytes > (1ull << 30)) return fail(RTX_ERR_INVALID, "bytes must be between 1 MiB and 1 GiB");
+    CU(cudaSetDevice(c->device));
+    const unsigned long long n_vec = bytes / 16;
+    uint4* buf = nullptr;
+    unsigned int* sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    cudaError_t err = cudaMalloc(&buf, n_vec * 16);
+    if (err == cudaSuccess) err = cudaMalloc(&sink, sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaMemsetAsync(buf, 0x5a, n_vec * 16, c->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(sink, 0, sizeof(unsigned int), c->stream);
+    if (err == cudaSuccess) err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
+    float best_ms = 0.f;
+    if (err == cudaSuccess) {
+        const unsigned grid = (unsigned)sms * 8u;
+        rtx::l2_read_kernel<<<grid, 256, 0, c->stream>>>(buf, n_vec, 2, sink);  // brings the buffer into L2
+        for (int attempt = 0; attempt < 3 && err == cudaSuccess; ++attempt) {
+            cudaEventRecord(e0, c->stream);
+            rtx::l2_read_kernel<<<grid, 256, 0, c->stream>>>(buf, n_vec, repeats, sink);
+            cudaEventRecord(e1, c->stream);
+            err = cudaEventSynchronize(e1);
+            float ms = 0.f;
+            if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+            if (err == cudaSuccess && (best_ms == 0.f || ms < best_ms)) best_ms = ms;
+        }
+        c->launches += 4;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (err != cudaSuccess) return cuda_fail(err, "rtx_ctx_measure_l2_read");
+    *gbytes_per_s = (double)(n_vec * 16) * (double)repeats / ((double)best_ms * 1e-3) / 1e9;
+    return RTX_OK;
+}
 int rtx_ctx_set_bvh_builder(rtx_ctx* c, int kind) {
     if (!c || kind < 0 || kind > 1) return fail(RTX_ERR_INVALID, "bad argument");
     c->bvh_builder = kind;

@@ -1383,4 +1383,28 @@ __global__ void reduce_tonemap_peers_kernel(float4* __restrict__ accum, PeerList
     out[i] = make_uchar4(quantise(a.x, inv), quantise(a.y, inv), quantise(a.z, inv), 255);
 }
 
+// ---------------------------------------------------------------------------
+// Measurement aid (rtx_ctx_measure_l2_read): every thread streams 16-byte words of a buffer that fits in L2,
+// `repeats` times over, with loads that bypass L1 (ld.global.cg). Four independent loads in flight per thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ buf, unsigned long long n_vec, int repeats,
+                                                      unsigned int* __restrict__ sink) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int acc = 0;
+    for (int r = 0; r < repeats; ++r) {
+        unsigned long long i = first;
+        for (; i + 3 * stride < n_vec; i += 4 * stride) {
+            const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+            acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+        }
+        for (; i < n_vec; i += stride) {
+            const uint4 a = __ldcg(buf + i);
+            acc ^= a.x ^ a.y ^ a.z ^ a.w;
+        }
+        acc = acc * 2654435761u + (unsigned int)r;  // keeps the passes from being merged
+    }
+    if (acc == 0x9e3779b9u) atomicAdd(sink, 1u);  // practically never; keeps the loads alive
+}
+
 }  // namespace rtx

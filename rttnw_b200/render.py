@@ -108,6 +108,12 @@ class Context:
         abi.check(self.lib.rtx_ctx_profile_read(self.h, C.byref(a), C.byref(b), C.byref(n), 1 if reset else 0))
         return {"shade_ms": a.value, "trace_ms": b.value, "iterations": n.value}
 
+    def measure_l2_read(self, nbytes: int = 0, repeats: int = 0) -> float:
+        """GB/s of 16-byte loads over an L2-resident buffer (the bandwidth roof of BVH-node traffic)."""
+        g = C.c_double()
+        abi.check(self.lib.rtx_ctx_measure_l2_read(self.h, nbytes, repeats, C.byref(g)))
+        return g.value
+
     def kernel_launches(self) -> int:
         n = C.c_uint64()
         abi.check(self.lib.rtx_ctx_kernel_launches(self.h, C.byref(n)))
