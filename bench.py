@@ -55,6 +55,24 @@ def workload(args):
     return d, w, h
 
 
+def issue_roof(ncu, pairs_per_step, ms_per_step, clocks, info):
+    """The roof that binds the wavefront (SURVEY.md §8d names it): warp instructions issued against the SMs' issue
+    slots (4 per clock and SM). Instruction counts per launch come from the committed ncu capture of the default
+    configuration (profiles/dram_traffic.json: three launches of each kernel across a frame of scene 9, 256 Ki slots);
+    the time and the SM clock are this run's."""
+    try:
+        w = ncu["wf_trace_kernel_warp_instructions"] + ncu["wf_shade_kernel_warp_instructions"]
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        slots = ms_per_step * 1e-3 * mhz * 1e6 * 4 * sms
+        return {"warp_instructions_per_iteration": w, "iterations_per_step": pairs_per_step, "issue_slots_per_step": slots,
+                "frac": w * pairs_per_step / slots, "lanes_active_trace": ncu["wf_trace_kernel_lanes_active_per_warp_instruction"],
+                "lanes_active_shade": ncu["wf_shade_kernel_lanes_active_per_warp_instruction"],
+                "note": "valid for the configuration the capture was taken on (scene 9, default pool); elsewhere indicative only"}
+    except Exception as e:  # no capture on file
+        return {"unavailable": str(e)}
+
+
 def config(args, d, w, h, extra=None):
     c = {"workload": f"scene {args.scene} ({d['name']}) {w}x{h}, max depth {d['max_depth']}, "
                      f"{args.spp} spp per GPU per step; reference default is {d['samples']} spp per frame",
@@ -412,6 +430,7 @@ def run_ours(args):
                     "l2": {"peak": l2_gbs, "unit": "GB/s", "frac": achieved / l2_gbs,
                            "peak_source": "rtx_ctx_measure_l2_read: 16-byte ld.global.cg over a 32 MiB L2-resident buffer, all SMs, this run"},
                     "ncu": {k: v for k, v in ncu.items() if k.startswith("wf_trace_kernel_") or k == "source"},
+                    "issue": issue_roof(ncu, trace_launches / args.steps, total_ms / args.steps, clocks, info),
                     "per_ray_means": {k: st[k] for k in ("box_tests", "node_visits", "sphere_tests", "rect_tests", "instance_enters", "medium_tests")},
                     "note": "the flattened scene (%.1f MB) and the path pool are L2-resident: the algorithmic bytes are the BVH-node and "
                             "primitive bytes the traversal must fetch, served by L1/L2, so HBM is not what bounds this kernel "
