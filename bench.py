@@ -170,13 +170,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Rows that arrived inside [t0, t1] (the timed region; a row reports the 200 ms before it). A region
+        shorter than the sampling period may hold none: then every row since start() — the warm-up steps run the
+        same load — is used and the window says so."""
         if self.proc:
             self.proc.terminate()
+        window = "timed region"
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.2)]
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -189,7 +196,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------
@@ -294,12 +301,10 @@ def run_ours(args):
         else:
             abi.check(lib.rtx_reduce_tonemap_peers(ctx.h, accum, None, 0, w, h, C.c_void_p(d_rgba.data_ptr())))
 
-    def timed(fn, steps, sample_clocks=False):
-        sampler = ClockSampler(local) if sample_clocks else None
+    def timed(fn, steps, sampler=None):
         barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
+        t0 = time.monotonic()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(steps):
@@ -311,9 +316,11 @@ def run_ours(args):
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), (sampler.stop() if sampler else None)
+        return ms.item(), (sampler.stop(t0, time.monotonic()) if sampler else None)
 
     # ---- device-resident throughput ----
+    sampler = ClockSampler(local)  # started ahead of the warm-up: nvidia-smi needs a few hundred ms to deliver its first row
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         flush.fill_(1)
         render_step(scene)
@@ -346,7 +353,7 @@ def run_ours(args):
     ctx.set_profiling(True)  # CUDA events around every shade / trace launch, on the launching stream
     ctx.profile_read(reset=True)
     launches0 = ctx.kernel_launches()
-    total_ms, clocks = timed(step_resident, args.steps, sample_clocks=True)
+    total_ms, clocks = timed(step_resident, args.steps, sampler)
     launches = ctx.kernel_launches() - launches0
     prof = ctx.profile_read(reset=True)
     ctx.set_profiling(False)
