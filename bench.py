@@ -61,6 +61,7 @@ def issue_roof(ncu, pairs_per_step, ms_per_step, clocks, info):
     configuration (profiles/dram_traffic.json: three launches of each kernel across a frame of scene 9, 256 Ki slots);
     the time and the SM clock are this run's."""
     try:
+        import torch
         w = ncu["wf_trace_kernel_warp_instructions"] + ncu["wf_shade_kernel_warp_instructions"]
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
         sms = torch.cuda.get_device_properties(0).multi_processor_count
