@@ -26,7 +26,6 @@ enum RecType : int32_t {
     REC_RECT_XY = 2,   // d = {a0, a1, b0, b1, k}  (axis0, axis1, k_axis) = (0,1,2)
     REC_RECT_XZ = 3,   //                                                   (0,2,1)
     REC_RECT_YZ = 4,   //                                                   (1,2,0)
-    REC_INSTANCE = 5,  // (unused: wrapped primitives carry their chain, see Record::c)
     REC_BOX = 7,       // Cube: d = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}; a = index of the first of its six rectangle
                        // records (Cube::new order), b = first primitive id
     REC_MEDIUM = 6     // a = phase texture, b = prim id, c = boundary BVH root, or -1: the boundary is the

@@ -18,9 +18,6 @@
 #ifndef K1_MINB
 #define K1_MINB 5  // 96 registers: 4.8 / 4.3 / 4.2 Grays/s on primary / secondary / tertiary rays of scene 9 (4, 6, 7 CTAs per SM: 4.3, 4.3, 4.5 on primaries)
 #endif
-#ifndef SHADE_DENSE
-#define SHADE_DENSE 0  // 1: camera rays generated densely through shared memory (three passes per CTA, measured below)
-#endif
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -91,16 +88,14 @@ struct Tally {
     __device__ __forceinline__ void node() {}
     __device__ __forceinline__ void sphere() {}
     __device__ __forceinline__ void rect() {}
-    __device__ __forceinline__ void instance() {}
     __device__ __forceinline__ void medium() {}
 };
 template <>
 struct Tally<true> {
-    uint32_t n_node = 0, n_sphere = 0, n_rect = 0, n_inst = 0, n_med = 0;
+    uint32_t n_node = 0, n_sphere = 0, n_rect = 0, n_med = 0;
     __device__ __forceinline__ void node() { ++n_node; }
     __device__ __forceinline__ void sphere() { ++n_sphere; }
     __device__ __forceinline__ void rect() { ++n_rect; }
-    __device__ __forceinline__ void instance() { ++n_inst; }
     __device__ __forceinline__ void medium() { ++n_med; }
 };
 
@@ -580,17 +575,16 @@ __global__ void __launch_bounds__(128, K1_MINB) trace_rays_kernel(SceneView sc, 
     }
     if constexpr (kCount) {
         // warp-reduce, one atomic per warp per counter
-        uint32_t vals[5] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst, tally.n_med};
+        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_med};
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < 4; ++k)
             for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], off);
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
             atomicAdd(&counters->box_tests, 2ull * vals[0]);
             atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
             atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
-            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
-            atomicAdd(&counters->medium_tests, (unsigned long long)vals[4]);
+            atomicAdd(&counters->medium_tests, (unsigned long long)vals[3]);
         }
     }
 }
@@ -1062,17 +1056,16 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
         if (lane == 0 && my_rays) atomicAdd(ray_count, my_rays);
     }
     if constexpr (kCount) {
-        uint32_t vals[5] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst, tally.n_med};
+        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_med};
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < 4; ++k)
             for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
         if (lane == 0) {
             atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
             atomicAdd(&counters->box_tests, 2ull * vals[0]);
             atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
             atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
-            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
-            atomicAdd(&counters->medium_tests, (unsigned long long)vals[4]);
+            atomicAdd(&counters->medium_tests, (unsigned long long)vals[3]);
         }
     }
 }
@@ -1121,16 +1114,11 @@ constexpr int kTraceBlock = WF_TRACE_BLOCK;  // trace kernel CTA (divides kWfBlo
 #define WF_SHADE_MINB 5
 #endif
 
-// Default (SHADE_DENSE 0): one pass — shade the hit, refill emptied slots per warp (one dispenser atomic per
-// warp), medium pre-pass, write the slot. Alternative (SHADE_DENSE 1), measured A/B on one box at a 2 Mi-slot
-// pool: scene 9 525 vs 536 M samples/s, scene 2 1127 vs 1181, scene 3 1513 vs 1611, scene 7 596 vs 581 —
-// the barriers cost more than the dense generation saves except on the Cornell box. Its three passes:
-//   1. every thread shades the hit of its own slot (one level of color()); finished paths add their
-//      sample to the image and put the slot on a shared-memory list;
-//   2. the first ceil(Q / 32) warps generate the Q new camera rays densely (one dispenser atomic per
-//      CTA; consecutive items = the pixels of one 8x4 tile at one sample index) and hand each to the
-//      thread that owns the slot through shared memory;
-//   3. every thread that now has a ray — scattered or new — runs the medium pre-pass and writes its slot.
+// One pass: shade the hit of the slot (one level of color()), add a finished path's sample to the image, refill
+// emptied slots per warp (one dispenser atomic per warp; 32 consecutive items = the pixels of one 8x4 tile at one
+// sample index), run the medium pre-pass for the new ray and write the slot. A three-pass variant that generated
+// the camera rays densely through shared memory was measured and dropped (the barriers cost more
+// than the dense generation saves, except on the Cornell box).
 template <bool kCount>
 __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBlock)) wf_shade_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out, Counters* counters) {
     const unsigned FULL = 0xffffffffu;
@@ -1138,21 +1126,8 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
     const int lane = tid & 31;
     const int i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < a.n_slots;
-#if SHADE_DENSE
-    __shared__ int s_queue[kShadeBlock];
-    __shared__ int s_count;
-    __shared__ unsigned long long s_base;
-    __shared__ double s_ray[7][kShadeBlock];
-    __shared__ uint32_t s_pix[2][kShadeBlock];
-    __shared__ unsigned char s_staged[kShadeBlock];
-#endif
     int32_t stack[kStackSize];  // only a ConstantMedium with a general boundary traverses here
     Tally<kCount> tally;
-#if SHADE_DENSE
-    if (tid == 0) s_count = 0;
-    s_staged[tid] = 0;
-    __syncthreads();
-#endif
 
     // ---- pass 1: shade ----
     int bounce = valid ? a.pool.bounce[i] : -2;
@@ -1186,57 +1161,6 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
             fresh = true;
         }
     }
-#if SHADE_DENSE
-    {   // empty slots (just emptied or empty before) queue up for a new path sample
-        const bool want = bounce == -1;
-        const unsigned m = __ballot_sync(FULL, want);
-        int wbase = 0;
-        if (lane == 0 && m != 0) wbase = atomicAdd(&s_count, __popc(m));
-        wbase = __shfl_sync(FULL, wbase, 0);
-        if (want) s_queue[wbase + __popc(m & ((1u << lane) - 1u))] = tid;
-    }
-    __syncthreads();
-
-    // ---- pass 2: new camera rays, densely ----
-    const int q = s_count;
-    if (q > 0) {
-        if (tid == 0) s_base = __ldcg(a.next_item) < a.total_items ? atomicAdd(a.next_item, (unsigned long long)q) : a.total_items;
-        __syncthreads();
-        const unsigned long long item = s_base + (unsigned long long)tid;
-        if (tid < q && item < a.total_items) {
-            // item -> (tile, sample, pixel of the tile)
-            const unsigned long long group = item >> 5;  // one (tile, sample) pair
-            const unsigned int tile = (unsigned int)(group / (unsigned long long)a.spp_count);
-            const unsigned int smp_i = (unsigned int)(group - (unsigned long long)tile * (unsigned long long)a.spp_count);
-            const int pi = (int)(item & 31ull);
-            const int px = (int)(tile % (unsigned int)a.tiles_x) * kTileW + (pi & (kTileW - 1));
-            const int row = (int)(tile / (unsigned int)a.tiles_x) * kTileH + (pi / kTileW);  // row 0 = top
-            if (px < a.width && row < a.height) {  // (a pixel beyond a ragged image edge: the slot retries next iteration)
-                Sampler s2{a.k0, a.k1, (uint32_t)(row * a.width + px), (uint32_t)a.spp_begin + smp_i, 0u};
-                RayD r2;
-                camera_ray(a.cam, a.width, a.height, px, a.height - 1 - row, s2, r2);
-                const int owner = s_queue[tid];
-                s_ray[0][owner] = r2.o.x; s_ray[1][owner] = r2.o.y; s_ray[2][owner] = r2.o.z;
-                s_ray[3][owner] = r2.d.x; s_ray[4][owner] = r2.d.y; s_ray[5][owner] = r2.d.z;
-                s_ray[6][owner] = r2.time;
-                s_pix[0][owner] = s2.pixel; s_pix[1][owner] = s2.sample;
-                s_staged[owner] = 1;
-            }
-        }
-        __syncthreads();
-        if (s_staged[tid]) {
-            ray.o = mk(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]);
-            ray.d = mk(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
-            ray.time = s_ray[6][tid];
-            smp.pixel = s_pix[0][tid];
-            smp.sample = s_pix[1][tid];
-            pc = PathColor{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
-            bounce = 0;
-            fresh = true;
-        }
-    }
-
-#else
     {   // ---- refill empty slots per warp: consecutive items are the 32 pixels of one tile at one sample index ----
         const bool want = bounce == -1;
         unsigned m = __ballot_sync(FULL, want);
@@ -1267,7 +1191,6 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
         }
     }
 
-#endif
     // ---- pass 3: the new ray: media first (their scatter point bounds the surface search), then out to the pool ----
     if (fresh) {
         smp.bounce = (uint32_t)bounce;
@@ -1322,16 +1245,15 @@ __global__ void __launch_bounds__(kTraceBlock, WF_TRACE_MINB * (128 / kTraceBloc
         if (lane == 0 && am != 0) atomicAdd(ray_count, (unsigned long long)__popc(am));
     }
     if constexpr (kCount) {
-        uint32_t vals[4] = {tally.n_node, tally.n_sphere, tally.n_rect, tally.n_inst};
+        uint32_t vals[3] = {tally.n_node, tally.n_sphere, tally.n_rect};
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 3; ++k)
             for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
         if (lane == 0) {
             atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
             atomicAdd(&counters->box_tests, 2ull * vals[0]);
             atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
             atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
-            atomicAdd(&counters->instance_enters, (unsigned long long)vals[3]);
         }
     }
 }
