@@ -1,4 +1,5 @@
-//! Raw bindings: one item per declaration of include/rttnw_b200.h (ABI version 1).
+//! Raw bindings: one item per declaration of include/rttnw_b200.h (ABI version 1; tests/test_host_cpu.py keeps the
+//! function names in step with the header).
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -137,6 +138,29 @@ pub struct rtx_render_params {
     pub seed: u64,
 }
 
+/// Mean per-ray work counters of the traversal (`rtx_trace_rays_stats`, `rtx_render_counted`).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct rtx_trace_stats {
+    pub rays: f64,
+    pub box_tests: f64,
+    pub node_visits: f64,
+    pub sphere_tests: f64,
+    pub rect_tests: f64,
+    pub instance_enters: f64,
+    pub medium_tests: f64,
+}
+/// The scene table of src/main.rs:66-183 and the defaults of :255.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rtx_scene_defaults {
+    pub width: i32,
+    pub height: i32,
+    pub samples: i32,
+    pub max_depth: i32,
+    pub name: *const c_char,
+}
+
 pub enum rtx_ctx {}
 pub enum rtx_scene {}
 
@@ -147,11 +171,20 @@ extern "C" {
     pub fn rtx_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut rtx_ctx) -> c_int;
     pub fn rtx_ctx_destroy(ctx: *mut rtx_ctx) -> c_int;
     pub fn rtx_ctx_sync(ctx: *mut rtx_ctx) -> c_int;
+    pub fn rtx_ctx_stream(ctx: *mut rtx_ctx) -> *mut c_void;
     pub fn rtx_ctx_set_bvh_builder(ctx: *mut rtx_ctx, kind: c_int) -> c_int;
+    pub fn rtx_ctx_kernel_launches(ctx: *mut rtx_ctx, out: *mut u64) -> c_int;
+    pub fn rtx_ctx_set_profiling(ctx: *mut rtx_ctx, on: c_int) -> c_int;
+    pub fn rtx_ctx_profile_read(ctx: *mut rtx_ctx, shade_ms: *mut f64, trace_ms: *mut f64, iterations: *mut u64, reset: c_int) -> c_int;
+    pub fn rtx_ctx_measure_l2_read(ctx: *mut rtx_ctx, bytes: u64, repeats: c_int, gbytes_per_s: *mut f64) -> c_int;
     pub fn rtx_scene_create(ctx: *mut rtx_ctx, desc: *const rtx_scene_desc, out: *mut *mut rtx_scene) -> c_int;
     pub fn rtx_scene_destroy(scene: *mut rtx_scene) -> c_int;
+    pub fn rtx_scene_info(scene: *const rtx_scene, n_bvh_nodes: *mut i32, n_records: *mut i32, n_xform_ops: *mut i32, device_bytes: *mut i64) -> c_int;
     pub fn rtx_trace_rays(ctx: *mut rtx_ctx, scene: *const rtx_scene, n: i64, rays: *const rtx_ray, hits: *mut rtx_hit) -> c_int;
+    pub fn rtx_trace_rays_device(ctx: *mut rtx_ctx, scene: *const rtx_scene, n: i64, d_rays: *const rtx_ray, d_hits: *mut rtx_hit) -> c_int;
+    pub fn rtx_trace_rays_stats(ctx: *mut rtx_ctx, scene: *const rtx_scene, n: i64, d_rays: *const rtx_ray, out: *mut rtx_trace_stats) -> c_int;
     pub fn rtx_render(ctx: *mut rtx_ctx, scene: *const rtx_scene, params: *const rtx_render_params, d_accum: *mut f32, d_ray_count: *mut u64) -> c_int;
+    pub fn rtx_render_counted(ctx: *mut rtx_ctx, scene: *const rtx_scene, params: *const rtx_render_params, d_accum: *mut f32, out: *mut rtx_trace_stats) -> c_int;
     pub fn rtx_tonemap_rgba8(ctx: *mut rtx_ctx, d_accum: *const f32, width: i32, height: i32, out: *mut u8, out_on_device: c_int) -> c_int;
     pub fn rtx_reduce_tonemap_peers(ctx: *mut rtx_ctx, d_accum: *mut f32, d_peer_accums: *const *const f32, n_peers: i32, width: i32, height: i32, d_rgba8: *mut u8) -> c_int;
     pub fn rtx_malloc(ctx: *mut rtx_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
@@ -159,4 +192,14 @@ extern "C" {
     pub fn rtx_memset_zero(ctx: *mut rtx_ctx, ptr: *mut c_void, bytes: usize) -> c_int;
     pub fn rtx_memcpy_h2d(ctx: *mut rtx_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
     pub fn rtx_memcpy_d2h(ctx: *mut rtx_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn rtx_ipc_export(ctx: *mut rtx_ctx, d_ptr: *mut c_void, handle_out: *mut u8) -> c_int;
+    pub fn rtx_ipc_open(ctx: *mut rtx_ctx, handle: *const u8, d_ptr_out: *mut *mut c_void) -> c_int;
+    pub fn rtx_ipc_close(ctx: *mut rtx_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn rtx_builtin_scene_defaults(scene_number: c_int, out: *mut rtx_scene_defaults) -> c_int;
+    pub fn rtx_builtin_scene(scene_number: c_int, seed: u64, earth_png_path: *const c_char, out: *mut *mut rtx_scene_desc) -> c_int;
+    pub fn rtx_scene_desc_free(desc: *mut rtx_scene_desc) -> c_int;
+    pub fn rtx_flatten_check(desc: *const rtx_scene_desc, n_bvh_nodes: *mut i32, n_records: *mut i32, n_prim_ids: *mut i32) -> c_int;
+    pub fn rtx_png_read_rgba8(path: *const c_char, width: *mut i32, height: *mut i32, rgba_out: *mut *mut u8) -> c_int;
+    pub fn rtx_png_write_rgba8(path: *const c_char, width: i32, height: i32, rgba: *const u8) -> c_int;
+    pub fn rtx_buffer_free(p: *mut c_void) -> c_int;
 }

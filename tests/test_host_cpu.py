@@ -31,6 +31,16 @@ def test_library_exports_every_declared_symbol():
     assert lib.rtx_abi_version() == 1
 
 
+def test_rust_bindings_declare_the_same_symbols():
+    """rust/rttnw-b200-sys cannot be compiled here (no Rust toolchain): at least keep its extern block and the
+    header in step, name by name."""
+    header = open(os.path.join(ROOT, "include", "rttnw_b200.h")).read()
+    declared = set(re.findall(r"\b(rtx_[a-z0-9_]+)\s*\(", header)) - {"rtx_status"}
+    ffi = open(os.path.join(ROOT, "rust", "rttnw-b200-sys", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (rtx_[a-z0-9_]+)", ffi))
+    assert bound == declared, (declared - bound, bound - declared)
+
+
 def test_struct_sizes_match_header():
     # the sizes written next to the typedefs in include/rttnw_b200.h
     assert C.sizeof(abi.Node) == 96 and C.sizeof(abi.Material) == 40 and C.sizeof(abi.Texture) == 48
