@@ -56,20 +56,24 @@ def workload(args):
 
 
 def issue_roof(ncu, pairs_per_step, ms_per_step, clocks, info):
-    """The roof that binds the wavefront (SURVEY.md §8d names it): warp instructions issued against the SMs' issue
-    slots (4 per clock and SM). Instruction counts per launch come from the committed ncu capture of the default
-    configuration (profiles/dram_traffic.json: three launches of each kernel across a frame of scene 9, 256 Ki slots);
-    the time and the SM clock are this run's."""
+    """Warp instructions issued against the SMs' issue slots (4 per clock and SM): how far the wavefront is from
+    the roof SURVEY.md §8d names first. Instruction counts per launch come from the committed ncu captures of the
+    default configuration (profiles/dram_traffic.json): three --set full captures from the expensive middle of a frame
+    of scene 9, scaled to the whole-render mean by the launch durations of profiles/r1_launches.csv (instructions
+    per microsecond are constant to within 10 % across launches, profiles/r1_first_quarter_instructions.csv).
+    The time and the SM clock are this run's. An estimate, good to about a tenth."""
     try:
         import torch
-        w = ncu["wf_trace_kernel_warp_instructions"] + ncu["wf_shade_kernel_warp_instructions"]
+        w = 0.0
+        for k in ("wf_trace_kernel", "wf_shade_kernel"):
+            w += ncu[k + "_warp_instructions"] * ncu[k + "_duration_us_mean_over_a_render"] / ncu[k + "_duration_us_alone"]
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
         sms = torch.cuda.get_device_properties(0).multi_processor_count
         slots = ms_per_step * 1e-3 * mhz * 1e6 * 4 * sms
-        return {"warp_instructions_per_iteration": w, "iterations_per_step": pairs_per_step, "issue_slots_per_step": slots,
+        return {"warp_instructions_per_iteration_mean": w, "iterations_per_step": pairs_per_step, "issue_slots_per_step": slots,
                 "frac": w * pairs_per_step / slots, "lanes_active_trace": ncu["wf_trace_kernel_lanes_active_per_warp_instruction"],
                 "lanes_active_shade": ncu["wf_shade_kernel_lanes_active_per_warp_instruction"],
-                "note": "valid for the configuration the capture was taken on (scene 9, default pool); elsewhere indicative only"}
+                "note": "estimate; valid for the configuration the captures were taken on (scene 9, default pool)"}
     except Exception as e:  # no capture on file
         return {"unavailable": str(e)}
 
