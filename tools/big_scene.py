@@ -4,7 +4,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import rttnw_b200 as R
 from rttnw_b200 import abi, scene as S
-from tests import _oracle as O
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 rng = np.random.default_rng(5)
@@ -17,7 +16,9 @@ print(f"{n} spheres: description built in {time.perf_counter() - t0:.2f} s", flu
 ctx = R.Context(0)
 m = 2_000_000
 o = rng.uniform(-side, side, (m, 3)); tgt = rng.uniform(-side, side, (m, 3))
-rays = O.make_rays(o, tgt - o)
+rays = np.zeros(m, dtype=abi.RAY_DTYPE)
+rays["origin"], rays["direction"] = o, tgt - o
+rays["t_min"], rays["t_max"], rays["xi"] = 0.001, np.finfo(np.float64).max, 0.5
 d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
 d_hits = torch.empty(m * 88, dtype=torch.uint8, device="cuda")
 res = {}
