@@ -210,3 +210,26 @@ def test_spp_sharding_reduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert b"OK" in outs[0][0]
+
+
+def test_committed_profile_counters_feed_the_bench_line():
+    """bench.py quotes ncu counters from profiles/dram_traffic.json (roofline.traffic / .ncu / .issue): the keys it
+    reads must be there, and the issue-slot estimate must come out of them without a GPU."""
+    import json
+    import bench
+    ncu = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+    for k in ("wf_trace_kernel", "wf_shade_kernel"):
+        for suffix in ("_dram_bytes_per_launch", "_warp_instructions", "_duration_us_alone", "_duration_us_mean_over_a_render",
+                       "_lanes_active_per_warp_instruction"):
+            assert ncu[k + suffix] > 0, k + suffix
+    import torch
+
+    class Props:
+        multi_processor_count = 148
+    real = torch.cuda.get_device_properties
+    torch.cuda.get_device_properties = lambda i: Props()
+    try:
+        r = bench.issue_roof(ncu, 1968.5, 136.5, {"sm_mhz": 1965.0}, {})
+    finally:
+        torch.cuda.get_device_properties = real
+    assert 0.3 < r["frac"] < 1.0, r
