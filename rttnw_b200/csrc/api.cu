@@ -77,6 +77,7 @@ struct rtx_ctx {
     unsigned long long* h_status = nullptr;      // pinned: [partition][parity] x {active, next_item}
     cudaEvent_t batch_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [partition][parity]
     int wf_batch = 8;
+    int wf_wide = 0;     // EXPERIMENTAL (RTX_BVH_WIDE=1): the trace kernel walks the 4-wide copy of the world BVH
     int wf_streams = 2;  // pool partitions driven concurrently on their own streams (RTX_WF_STREAMS, at most 4)
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> join_events;
@@ -152,6 +153,7 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->pool_slots_wanted = env_int("RTX_WF_SLOTS", c->pool_slots_wanted);
     c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
     c->wf_streams = std::min(4, env_int("RTX_WF_STREAMS", c->wf_streams));
+    c->wf_wide = env_int("RTX_BVH_WIDE", c->wf_wide);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
     if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : 0;
     // the traversal stack lives in local memory: prefer L1 over shared for it
@@ -423,6 +425,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->view.images = (const rtx::DImage*)(base + off_images);
     s->view.media = (const rtx::DMedium*)(base + off_media);
     s->view.world_root = fs.world_root;
+    s->view.wide_root = fs.world_deferred ? -1 : fs.wide_root;
     s->view.n_media = fs.n_media;
     s->camera = fs.camera;
     s->n_nodes = (int32_t)(host_nodes + lbvh_nodes);
@@ -602,6 +605,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     CU(cudaMemsetAsync(c->d_next_item, 0, sizeof(unsigned long long), c->stream));
     float4* acc = reinterpret_cast<float4*>(d_accum);
     const int batch = c->wf_batch;
+    const bool wide = c->wf_wide != 0 && s->view.wide_root >= 0;
     // P partitions of the pool, each driven on its own stream: the shade kernel of one partition (latency bound,
     // streams the pool) can share the SMs with the trace kernel of another (issue bound). Partition 0 runs on the
     // ctx stream; the others fork from it here and join it at the end.
@@ -671,12 +675,18 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                     rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
                     CU(prof_mark());
                     CU(prof_mark());
-                    rtx::wf_trace_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
+                    if (wide)
+                        rtx::wf_trace_kernel<true, true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
+                    else
+                        rtx::wf_trace_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
                 } else {
                     rtx::wf_shade_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
                     CU(prof_mark());
                     CU(prof_mark());
-                    rtx::wf_trace_kernel<false><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
+                    if (wide)
+                        rtx::wf_trace_kernel<false, true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
+                    else
+                        rtx::wf_trace_kernel<false><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
                 }
                 CU(prof_mark());
             }

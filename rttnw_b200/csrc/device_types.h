@@ -122,6 +122,7 @@ struct SceneView {
     const DMedium* media;
     int32_t world_root;
     int32_t n_media;  // > 0: rays draw one Philox MEDIUM block per 4 media
+    int32_t wide_root;  // >= 0: the world BVH once more, 4-wide (a node = the two consecutive entries at this index)
 };
 
 // Camera::new precomputed on the host in f64 exactly as camera.rs:32-61 does.

@@ -76,6 +76,7 @@ struct BvhBuilder {
         Aabb box;
         int left = -1, right = -1;
         int first = 0, count = 0;
+        int32_t leaf_code = 0;  // set by emit_leaf (leaf codes are negative)
     };
     std::vector<Tmp> tmp;
     // what the builder touches per primitive, packed and partitioned in place (the Items are 144 bytes apart)
@@ -202,10 +203,11 @@ struct BvhBuilder {
         set_child_box(n, which, e);
         (which == 0 ? n.child0 : n.child1) = kEmptyChild;
     }
-    int32_t emit_leaf(const Tmp& t) {
+    int32_t emit_leaf(Tmp& t) {
         int32_t first = (int32_t)records.size();
         for (int i = 0; i < t.count; ++i) records.push_back(items[(size_t)prims[(size_t)(t.first + i)].idx].rec);
-        return ~((first << 4) | t.count);
+        t.leaf_code = ~((first << 4) | t.count);
+        return t.leaf_code;
     }
     int depth = 0;  // inner nodes on the longest root-to-leaf path (set by build)
     int32_t emit(int ti, int level = 1) {  // ti is an inner tmp node
@@ -214,14 +216,54 @@ struct BvhBuilder {
         nodes.push_back(BvhNode{});
         int kids[2] = {tmp[(size_t)ti].left, tmp[(size_t)ti].right};
         for (int k = 0; k < 2; ++k) {
-            const Tmp ct = tmp[(size_t)kids[k]];
-            int32_t ref = ct.left < 0 ? emit_leaf(ct) : emit(kids[k], level + 1);
+            const bool leaf = tmp[(size_t)kids[k]].left < 0;
+            int32_t ref = leaf ? emit_leaf(tmp[(size_t)kids[k]]) : emit(kids[k], level + 1);
             BvhNode& n = nodes[(size_t)idx];
-            set_child_box(n, k, ct.box);
+            set_child_box(n, k, tmp[(size_t)kids[k]].box);
             (k == 0 ? n.child0 : n.child1) = ref;
         }
         return idx;
     }
+    // The same tree with every other level collapsed: a 4-wide node is TWO consecutive BvhNode entries (128 bytes,
+    // even index), its up to four children the grandchildren of the binary node (a child that is a leaf stays a
+    // child). Child references are leaf codes (the binary tree's: the records are shared) or the index of the first
+    // entry of another wide node. Call after emit(). Returns that index; wide_depth counts wide levels.
+    int wide_depth = 0;
+    int32_t emit_wide(int ti, int level = 1) {
+        wide_depth = std::max(wide_depth, level);
+        int kids[4], nk = 0;
+        const int two[2] = {tmp[(size_t)ti].left, tmp[(size_t)ti].right};
+        for (int k = 0; k < 2; ++k) {
+            const Tmp& c = tmp[(size_t)two[k]];
+            if (c.left < 0) {
+                kids[nk++] = two[k];
+            } else {
+                kids[nk++] = c.left;
+                kids[nk++] = c.right;
+            }
+        }
+        if (nodes.size() & 1) {  // 128-byte alignment of the pair: an unreferenced filler entry
+            nodes.push_back(BvhNode{});
+            set_child_empty(nodes.back(), 0);
+            set_child_empty(nodes.back(), 1);
+        }
+        const int32_t idx = (int32_t)nodes.size();
+        nodes.push_back(BvhNode{});
+        nodes.push_back(BvhNode{});
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nk) {
+                set_child_empty(nodes[(size_t)idx + (size_t)(j >> 1)], j & 1);
+                continue;
+            }
+            const bool leaf = tmp[(size_t)kids[j]].left < 0;
+            const int32_t ref = leaf ? tmp[(size_t)kids[j]].leaf_code : emit_wide(kids[j], level + 1);
+            BvhNode& n = nodes[(size_t)idx + (size_t)(j >> 1)];
+            set_child_box(n, j & 1, tmp[(size_t)kids[j]].box);
+            ((j & 1) == 0 ? n.child0 : n.child1) = ref;
+        }
+        return idx;
+    }
+    int root_tmp = -1;  // the root of the last build() when it is an inner node
     // Returns the root node index; `bounds` gets the f64 bounds of everything.
     int32_t build(Aabb& bounds) {
         bounds.reset();
@@ -253,6 +295,7 @@ struct BvhBuilder {
             set_child_empty(nodes[(size_t)idx], 1);
             return idx;
         }
+        root_tmp = root;
         return emit(root);
     }
 };
@@ -561,6 +604,10 @@ struct Flattener {
             BvhBuilder b(out.nodes, out.records, w.items);
             root = b.build(bounds);
             out.max_stack = std::max(out.max_stack, 1 + b.depth + 1);
+            if (!w.is_boundary && b.root_tmp >= 0) {  // the 4-wide copy of the world BVH (opt-in traversal, RTX_BVH_WIDE)
+                const int32_t wide = b.emit_wide(b.root_tmp);
+                if (1 + 3 * b.wide_depth + 1 <= kTraversalStack) out.wide_root = wide;  // up to three siblings deferred per level
+            }
         }
         // media: records outside every BVH + a bounds list (only the main world has any)
         for (auto& m : w.media) {
@@ -708,6 +755,7 @@ struct Checker {
     const FlatScene& fs;
     std::string& err;
     std::vector<int> node_seen, rec_seen;
+    std::vector<int> leaf_rec = {}, wide_rec = {};  // records found in leaves of the binary trees / of the 4-wide world tree
     bool fail(const std::string& m) { err = m; return false; }
 
     static bool inside(const float lo[3], const float hi[3], const Aabb& b) {
@@ -794,6 +842,7 @@ struct Checker {
                 for (int i = 0; i < count; ++i) {
                     const Record& r = fs.records[(size_t)(first + i)];
                     if (rec_seen[(size_t)(first + i)]++) return fail("record reachable twice");
+                    if (!leaf_rec.empty()) leaf_rec[(size_t)(first + i)]++;
                     n_records++;
                     Aabb b;
                     if (record_box(r, b)) {
@@ -814,13 +863,57 @@ struct Checker {
         }
         return true;
     }
+    // The 4-wide copy of the world BVH: node `ni` is the pair of entries ni, ni + 1. Every child box must hold what is
+    // below it; the leaves are the binary tree's leaf codes.
+    bool walk_wide(int32_t ni, int depth) {
+        if (ni < 0 || ni + 1 >= (int32_t)fs.nodes.size() || (ni & 1)) return fail("wide node index out of range or odd");
+        if (depth > 64) return fail("wide BVH deeper than 64");
+        if (node_seen[(size_t)ni]++ || node_seen[(size_t)ni + 1]++) return fail("wide node reachable twice");
+        for (int j = 0; j < 4; ++j) {
+            const BvhNode& n = fs.nodes[(size_t)ni + (size_t)(j >> 1)];
+            const int k = j & 1;
+            const int32_t ref = k == 0 ? n.child0 : n.child1;
+            float lo[3] = {k == 0 ? n.c0x[0] : n.c1x[0], k == 0 ? n.c0y[0] : n.c1y[0], k == 0 ? n.c0z[0] : n.c1z[0]};
+            float hi[3] = {k == 0 ? n.c0x[1] : n.c1x[1], k == 0 ? n.c0y[1] : n.c1y[1], k == 0 ? n.c0z[1] : n.c1z[1]};
+            if (ref >= 0) {
+                if (ref + 1 >= (int32_t)fs.nodes.size()) return fail("wide child out of range");
+                for (int q = 0; q < 4; ++q) {
+                    const BvhNode& c = fs.nodes[(size_t)ref + (size_t)(q >> 1)];
+                    if (((q & 1) == 0 ? c.child0 : c.child1) == kEmptyChild) continue;
+                    const float clo[3] = {(q & 1) == 0 ? c.c0x[0] : c.c1x[0], (q & 1) == 0 ? c.c0y[0] : c.c1y[0], (q & 1) == 0 ? c.c0z[0] : c.c1z[0]};
+                    const float chi[3] = {(q & 1) == 0 ? c.c0x[1] : c.c1x[1], (q & 1) == 0 ? c.c0y[1] : c.c1y[1], (q & 1) == 0 ? c.c0z[1] : c.c1z[1]};
+                    for (int i = 0; i < 3; ++i)
+                        if (!(clo[i] >= lo[i] && chi[i] <= hi[i])) return fail("wide child box not inside its parent box");
+                }
+                if (!walk_wide(ref, depth + 1)) return false;
+            } else {
+                const int32_t v = ~ref;
+                const int first = v >> 4, count = v & 15;
+                if (first < 0 || first + count > (int)fs.records.size()) return fail("wide leaf range out of bounds");
+                for (int i = 0; i < count; ++i) {
+                    Aabb b;
+                    if (!record_box(fs.records[(size_t)(first + i)], b)) return fail("unknown record type in a wide leaf");
+                    if (!inside(lo, hi, b)) return fail("record not inside its wide leaf box");
+                    wide_rec[(size_t)(first + i)]++;
+                }
+            }
+        }
+        return true;
+    }
 };
 }  // namespace
 
 bool check_flat_scene(const FlatScene& fs, std::string& err) {
     Checker c{fs, err, std::vector<int>(fs.nodes.size(), 0), std::vector<int>(fs.records.size(), 0)};
     int n = 0;
+    c.leaf_rec.assign(fs.records.size(), 0);
     if (!c.walk(fs.world_root, 0, n)) return false;
+    if (fs.wide_root >= 0) {  // the 4-wide copy reaches exactly the records of the world's leaves, once each
+        c.wide_rec.assign(fs.records.size(), 0);
+        if (!c.walk_wide(fs.wide_root, 0)) return false;
+        if (c.wide_rec != c.leaf_rec) { err = "the 4-wide BVH does not reach the same records as the binary one"; return false; }
+    }
+    c.leaf_rec.clear();  // (boundary BVHs below have no wide copy)
     for (const DMedium& m : fs.media) {  // media: listed, not in a BVH; their boundary BVHs are walked here
         if (m.record < 0 || m.record >= (int32_t)fs.records.size()) { err = "medium record out of range"; return false; }
         const Record& r = fs.records[(size_t)m.record];
@@ -833,8 +926,11 @@ bool check_flat_scene(const FlatScene& fs, std::string& err) {
     if (fs.max_stack > kTraversalStack) { err = "BVH too deep for the traversal stack"; return false; }
     for (size_t i = 0; i < fs.records.size(); ++i)
         if (c.rec_seen[i] != 1) { err = "record not reachable from the world root"; return false; }
-    for (size_t i = 0; i < fs.nodes.size(); ++i)
-        if (c.node_seen[i] != 1) { err = "node not reachable from the world root"; return false; }
+    for (size_t i = 0; i < fs.nodes.size(); ++i) {
+        const BvhNode& nd = fs.nodes[i];
+        const bool filler = nd.child0 == kEmptyChild && nd.child1 == kEmptyChild && fs.wide_root >= 0;  // alignment entries of the wide copy
+        if (c.node_seen[i] != 1 && !(filler && c.node_seen[i] == 0)) { err = "node not reachable from the world root"; return false; }
+    }
     return true;
 }
 

@@ -319,6 +319,82 @@ __device__ __forceinline__ void traverse_simple(const SceneView& sc, int32_t roo
     }
 }
 
+// EXPERIMENTAL (RTX_BVH_WIDE=1; built and checked on the host, not yet measured on a GPU): the same query over the
+// 4-wide copy of the world BVH (flatten.cpp emit_wide). A node is two consecutive 64-byte entries: four child boxes
+// are tested per step, the hits ordered by entry distance with a five-exchange network, the nearest entered and
+// the others deferred farthest first. Half the dependent fetches of the binary loop per leaf reached.
+__device__ __forceinline__ void order2(float& ta, int32_t& ra, float& tb, int32_t& rb) {
+    const bool sw = tb < ta;
+    const float t = sw ? tb : ta;
+    const int32_t r = sw ? rb : ra;
+    tb = sw ? ta : tb;
+    rb = sw ? ra : rb;
+    ta = t;
+    ra = r;
+}
+template <bool kCount>
+__device__ __forceinline__ void traverse_wide(const SceneView& sc, int32_t root, const RayD& ray, double tmin, Best& best,
+                                              int32_t* stack, Tally<kCount>& tally) {
+    SlabRay s;
+    make_slab(ray.o, ray.d, s);
+    const float tmin_f = __double2float_rd(tmin);
+    float tmax_f = __double2float_ru(best.t);
+    int32_t* top = stack;
+    *top++ = kSentinel;
+    int32_t cur = root;
+    const float kMiss = __int_as_float(0x7f800000);  // +inf
+    while (true) {
+        while (cur >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            float t0, t1, t2, t3;
+            int32_t r0, r1, r2, r3;
+            {
+                float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                int4 meta = __ldg(reinterpret_cast<const int4*>(np + 3));
+                bool h0 = slab(s, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, tmin_f, tmax_f, t0);
+                bool h1 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, t1);
+                t0 = h0 ? t0 : kMiss; t1 = h1 ? t1 : kMiss;
+                r0 = meta.x; r1 = meta.y;
+            }
+            {
+                float4 q0 = __ldg(np + 4), q1 = __ldg(np + 5), q2 = __ldg(np + 6);
+                int4 meta = __ldg(reinterpret_cast<const int4*>(np + 7));
+                bool h2 = slab(s, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, tmin_f, tmax_f, t2);
+                bool h3 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, t3);
+                t2 = h2 ? t2 : kMiss; t3 = h3 ? t3 : kMiss;
+                r2 = meta.x; r3 = meta.y;
+            }
+            tally.node();
+            tally.node();  // two 64-byte entries, four box tests
+            order2(t0, r0, t1, r1);
+            order2(t2, r2, t3, r3);
+            order2(t0, r0, t2, r2);
+            order2(t1, r1, t3, r3);
+            order2(t1, r1, t2, r2);
+            // ascending now, the misses (+inf) last: defer the far hits, farthest first
+            if (t3 < kMiss) *top++ = r3;
+            if (t2 < kMiss) *top++ = r2;
+            if (t1 < kMiss) *top++ = r1;
+            cur = t0 < kMiss ? r0 : *--top;
+        }
+        if (cur == kSentinel) break;
+        int32_t v = ~cur;
+        int32_t first = v >> 4, count = v & 15;
+        cur = *--top;
+        for (int32_t i = 0; i < count; ++i) {
+            int4 h = __ldg(reinterpret_cast<const int4*>(sc.records + first + i));
+            double t;
+            int32_t hit_rec;
+            if (test_geometry(sc, first + i, h, ray, tmin, best.t, t, hit_rec, tally)) {
+                best.t = t;
+                best.rec = hit_rec;
+                best.chain = h.w;
+                tmax_f = __double2float_ru(t);
+            }
+        }
+    }
+}
+
 // ConstantMedium::hit, hittable.rs:740-796 (Q16), for the medium record `ri`: the scatter distance as
 // a candidate in [tmin, tmax]. `u` is the uniform variate the reference draws at :765.
 template <bool kPrecise, bool kCount>
@@ -1221,7 +1297,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
     }
 }
 
-template <bool kCount>
+template <bool kCount, bool kWide = false>
 __global__ void __launch_bounds__(kTraceBlock, WF_TRACE_MINB * (128 / kTraceBlock)) wf_trace_kernel(SceneView sc, PathPool pool, int n_slots, unsigned long long* ray_count,
                                                             Counters* counters) {
     const unsigned FULL = 0xffffffffu;
@@ -1233,7 +1309,8 @@ __global__ void __launch_bounds__(kTraceBlock, WF_TRACE_MINB * (128 / kTraceBloc
     if (act) {
         RayD ray{mk(pool.ox[i], pool.oy[i], pool.oz[i]), mk(pool.dx[i], pool.dy[i], pool.dz[i]), pool.time[i]};
         Best best{pool.best_t[i], -1, 0};
-        traverse_simple(sc, sc.world_root, ray, 0.001, best, stack, 0, tally);
+        if constexpr (kWide) traverse_wide(sc, sc.wide_root, ray, 0.001, best, stack, tally);
+        else traverse_simple(sc, sc.world_root, ray, 0.001, best, stack, 0, tally);
         if (best.rec >= 0) {  // closer than the medium candidate (if any) the shade kernel left there
             pool.best_t[i] = best.t;
             pool.best_rec[i] = best.rec;

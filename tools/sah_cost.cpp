@@ -36,6 +36,21 @@ static void walk(const FlatScene& fs, int32_t ref, double area, int depth, Acc& 
     walk(fs, n.child1, half_area(lo1, hi1), depth + 1, a);
 }
 
+// the 4-wide copy: node = entries ni, ni + 1; a step tests four boxes
+static void walk_wide(const FlatScene& fs, int32_t ni, double area, int depth, Acc& a) {
+    if (depth > a.depth) a.depth = depth;
+    a.node_area += area; a.nodes++;
+    for (int j = 0; j < 4; ++j) {
+        const BvhNode& n = fs.nodes[(size_t)ni + (size_t)(j >> 1)];
+        const int32_t ref = (j & 1) == 0 ? n.child0 : n.child1;
+        float lo[3] = {(j & 1) == 0 ? n.c0x[0] : n.c1x[0], (j & 1) == 0 ? n.c0y[0] : n.c1y[0], (j & 1) == 0 ? n.c0z[0] : n.c1z[0]};
+        float hi[3] = {(j & 1) == 0 ? n.c0x[1] : n.c1x[1], (j & 1) == 0 ? n.c0y[1] : n.c1y[1], (j & 1) == 0 ? n.c0z[1] : n.c1z[1]};
+        const double ar = half_area(lo, hi);
+        if (ref >= 0) walk_wide(fs, ref, ar, depth + 1, a);
+        else if (ref != kEmptyChild) { a.leaf_area += ar; a.prim_area += ar * ((~ref) & 15); a.leaves++; a.prims += (~ref) & 15; }
+    }
+}
+
 int main(int argc, char** argv) {
     int number = argc > 1 ? atoi(argv[1]) : 9;
     rttnw::SceneBuilder builder;
@@ -54,6 +69,12 @@ int main(int argc, char** argv) {
     printf("scene %d: %d nodes, %d leaves, %d leaf records, depth %d | expected per random ray through the root box: "
            "%.3f node steps, %.3f leaf visits, %.3f primitive tests\n",
            number, a.nodes, a.leaves, a.prims, a.depth, a.node_area / root, a.leaf_area / root, a.prim_area / root);
+    if (fs.wide_root >= 0) {
+        Acc w;
+        walk_wide(fs, fs.wide_root, root, 1, w);
+        printf("  4-wide copy: %d nodes, %d leaves, depth %d | %.3f node steps (4 boxes each), %.3f leaf visits, %.3f primitive tests\n",
+               w.nodes, w.leaves, w.depth, w.node_area / root, w.leaf_area / root, w.prim_area / root);
+    }
     if (argc > 2) {
         printf("  node steps by depth:");
         for (int d = 1; d <= a.depth; ++d) printf(" %.2f", a.by_depth[d] / root);
