@@ -77,7 +77,7 @@ struct rtx_ctx {
     unsigned long long* h_status = nullptr;      // pinned: [partition][parity] x {active, next_item}
     cudaEvent_t batch_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [partition][parity]
     int wf_batch = 8;
-    int wf_wide = 0;     // EXPERIMENTAL (RTX_BVH_WIDE=1): the trace kernel walks the 4-wide copy of the world BVH
+    int wf_wide = 0;     // RTX_BVH_WIDE=1: the trace kernel walks the 4-wide copy of the world BVH (measured slower: DESIGN.md §4)
     int wf_streams = 2;  // pool partitions driven concurrently on their own streams (RTX_WF_STREAMS, at most 4)
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> join_events;

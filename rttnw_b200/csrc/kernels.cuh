@@ -319,10 +319,12 @@ __device__ __forceinline__ void traverse_simple(const SceneView& sc, int32_t roo
     }
 }
 
-// EXPERIMENTAL (RTX_BVH_WIDE=1; built and checked on the host, not yet measured on a GPU): the same query over the
-// 4-wide copy of the world BVH (flatten.cpp emit_wide). A node is two consecutive 64-byte entries: four child boxes
-// are tested per step, the hits ordered by entry distance with a five-exchange network, the nearest entered and
-// the others deferred farthest first. Half the dependent fetches of the binary loop per leaf reached.
+// Opt-in (RTX_BVH_WIDE=1): the same query over the 4-wide copy of the world BVH (flatten.cpp emit_wide). A node is
+// two consecutive 64-byte entries: four child boxes are tested per step, the hits ordered by entry distance with a
+// five-exchange network, the nearest entered and the others deferred farthest first. Half the dependent fetches of
+// the binary loop per leaf reached, but 140 SASS instructions per step against 68, and all four boxes are tested
+// where the binary loop prunes a pair with its parent: measured 536 M samples/s against 600 M on scene 9 (same
+// hits: tests/test_gpu_parity.py::test_wide_bvh_traversal_finds_the_same_hits). Not the default.
 __device__ __forceinline__ void order2(float& ta, int32_t& ra, float& tb, int32_t& rb) {
     const bool sw = tb < ta;
     const float t = sw ? tb : ta;
