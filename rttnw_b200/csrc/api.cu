@@ -264,7 +264,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     CU(cudaSetDevice(c->device));
     rtx::FlatScene fs;
     std::string err;
-    if (!rtx::flatten_scene(*desc, fs, err, c->bvh_builder == 1)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    if (!rtx::flatten_scene(*desc, fs, err, c->bvh_builder == 1, c->wf_wide != 0)) return fail(RTX_ERR_INVALID, "scene description: " + err);
     // nodes the device builder will add behind the host-built ones (medium boundaries), and its box upload
     const size_t host_nodes = fs.nodes.size();
     const size_t lbvh_nodes = fs.world_deferred ? (size_t)fs.world_count - 1 : 0;
@@ -954,7 +954,7 @@ int rtx_flatten_check(const rtx_scene_desc* desc, int32_t* n_bvh_nodes, int32_t*
     if (!desc) return fail(RTX_ERR_INVALID, "desc is NULL");
     rtx::FlatScene fs;
     std::string err;
-    if (!rtx::flatten_scene(*desc, fs, err)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    if (!rtx::flatten_scene(*desc, fs, err, false, true)) return fail(RTX_ERR_INVALID, "scene description: " + err);  // with the 4-wide copy, to check it too
     if (!rtx::check_flat_scene(fs, err)) return fail(RTX_ERR_INVALID, "flattened scene invariant violated: " + err);
     if (n_bvh_nodes) *n_bvh_nodes = (int32_t)fs.nodes.size();
     if (n_records) *n_records = (int32_t)fs.records.size();

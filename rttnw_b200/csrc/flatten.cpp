@@ -323,6 +323,7 @@ struct Flattener {
     int next_prim = 0, next_medium = 0;
     double t_a = 0, t_b = 1;  // time interval moving-sphere bounds must cover
     bool defer_world = false;
+    bool wide_copy = false;  // also emit the 4-wide copy of the world BVH
 
     Flattener(const rtx_scene_desc& desc, FlatScene& o, std::string& e) : d(desc), out(o), err(e) {}
 
@@ -604,7 +605,7 @@ struct Flattener {
             BvhBuilder b(out.nodes, out.records, w.items);
             root = b.build(bounds);
             out.max_stack = std::max(out.max_stack, 1 + b.depth + 1);
-            if (!w.is_boundary && b.root_tmp >= 0) {  // the 4-wide copy of the world BVH (opt-in traversal, RTX_BVH_WIDE)
+            if (wide_copy && !w.is_boundary && b.root_tmp >= 0) {  // the 4-wide copy of the world BVH (opt-in traversal, RTX_BVH_WIDE)
                 const int32_t wide = b.emit_wide(b.root_tmp);
                 if (1 + 3 * b.wide_depth + 1 <= kTraversalStack) out.wide_root = wide;  // up to three siblings deferred per level
             }
@@ -703,10 +704,11 @@ struct Flattener {
 
 }  // namespace
 
-bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err, bool defer_world_bvh) {
+bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err, bool defer_world_bvh, bool wide_copy) {
     out = FlatScene();
     Flattener f(desc, out, err);
     f.defer_world = defer_world_bvh;
+    f.wide_copy = wide_copy;
     return f.run();
 }
 

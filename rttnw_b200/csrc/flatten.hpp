@@ -45,7 +45,8 @@ struct FlatScene {
 
 // Returns false and fills `err` on malformed input.
 // defer_world_bvh: leave the BVH over the world to the device builder when the world has at least two items.
-bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err, bool defer_world_bvh = false);
+// wide_copy: append the 4-wide copy of the (host-built) world BVH to the node array and set wide_root.
+bool flatten_scene(const rtx_scene_desc& desc, FlatScene& out, std::string& err, bool defer_world_bvh = false, bool wide_copy = false);
 
 // Structural invariants of the result (every record inside every ancestor box, every
 // record reachable exactly once per BVH, leaf sizes). Host logic test hook.

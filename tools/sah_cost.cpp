@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
     if (!rttnw::builtin_scene(number, 0, "assets/earth.png", builder)) { fprintf(stderr, "no scene %d\n", number); return 1; }
     FlatScene fs;
     std::string err;
-    if (!flatten_scene(builder.desc, fs, err)) { fprintf(stderr, "flatten: %s\n", err.c_str()); return 1; }
+    if (!flatten_scene(builder.desc, fs, err, false, true)) { fprintf(stderr, "flatten: %s\n", err.c_str()); return 1; }
     const BvhNode& r = fs.nodes[(size_t)fs.world_root];
     float lo[3], hi[3];
     lo[0] = std::min(r.c0x[0], r.c1x[0]); hi[0] = std::max(r.c0x[1], r.c1x[1]);
