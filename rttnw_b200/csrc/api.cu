@@ -15,6 +15,7 @@
 #include "flatten.hpp"
 #include "kernels.cuh"
 #include "lbvh.cuh"
+#include "trace2.cuh"
 #include "scene_api.hpp"
 
 namespace {
@@ -79,6 +80,12 @@ struct rtx_ctx {
     int wf_batch = 8;
     int wf_wide = 0;     // RTX_BVH_WIDE=1: the trace kernel walks the 4-wide copy of the world BVH (measured slower: DESIGN.md §4)
     int wf_streams = 2;  // pool partitions driven concurrently on their own streams (RTX_WF_STREAMS, at most 4)
+    // trace kernel form (RTX_TRACE): 2 = world BVH + stacks in shared memory, persistent warps (trace2.cuh), used when the
+    // BVH is shallow enough for the shared stack; 1 = the first form (wf_trace_kernel), always available
+    int trace_form = 2;
+    int trace_threads = 896;               // CTA size of the shared-memory form, one CTA per SM (RTX_TRACE_THREADS: 896, 640, 512, 448)
+    int t_leaf = 33, t_refill = 33, t_burst = 1 << 30;  // its vote thresholds (RTX_T_LEAF / RTX_T_REFILL / RTX_T_BURST)
+    int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> join_events;
     cudaEvent_t fork_event = nullptr;
@@ -103,6 +110,7 @@ struct rtx_scene {
     size_t arena_bytes = 0, arena_capacity = 0;
     std::vector<ArraySlot> images;
     int32_t n_nodes = 0, n_records = 0, n_xforms = 0;
+    int32_t world_first_node = 0, world_node_count = 0, world_depth = 0;  // the world BVH's node range (root first) and depth
 };
 
 extern "C" {
@@ -154,6 +162,12 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->wf_batch = env_int("RTX_WF_BATCH", c->wf_batch);
     c->wf_streams = std::min(4, env_int("RTX_WF_STREAMS", c->wf_streams));
     c->wf_wide = env_int("RTX_BVH_WIDE", c->wf_wide);
+    c->trace_form = env_int("RTX_TRACE", c->trace_form);
+    c->trace_threads = env_int("RTX_TRACE_THREADS", c->trace_threads);
+    c->t_leaf = env_int("RTX_T_LEAF", c->t_leaf);
+    c->t_refill = env_int("RTX_T_REFILL", c->t_refill);
+    c->t_burst = env_int("RTX_T_BURST", c->t_burst);
+    cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
     if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : 0;
     // the traversal stack lives in local memory: prefer L1 over shared for it
@@ -414,6 +428,9 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
         if (1 + depth + 1 > rtx::kTraversalStack)
             return bail(fail(RTX_ERR_UNSUPPORTED, "device-built BVH deeper than the traversal stack: use the host builder"));
         fs.world_root = (int32_t)host_nodes;
+        fs.world_first_node = (int32_t)host_nodes;
+        fs.world_node_count = (int32_t)lbvh_nodes;
+        fs.world_depth = depth;
     }
     s->view.nodes = (const rtx::BvhNode*)(base + off_nodes);
     s->view.records = (const rtx::Record*)(base + off_records);
@@ -431,6 +448,9 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->n_nodes = (int32_t)(host_nodes + lbvh_nodes);
     s->n_records = (int32_t)fs.records.size();
     s->n_xforms = (int32_t)fs.xforms.size();
+    s->world_first_node = fs.world_first_node;
+    s->world_node_count = fs.world_node_count;
+    s->world_depth = fs.world_depth;
     *out = s;
     return RTX_OK;
 }
@@ -640,6 +660,52 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             for (int q = 1; q < P; ++q) CU(cudaStreamWaitEvent(parts[(size_t)q].stream, c->fork_event, 0));
         }
     }
+    // ---- which trace kernel: the shared-memory form when the world BVH is shallow enough for its shared stack ----
+    rtx::TraceCfg tcfg{};
+    int t2_threads = 0;  // 0: first form
+    size_t t2_smem = 0;
+    unsigned t2_grid_cap = (unsigned)c->sm_count;
+    if (c->trace_form >= 2 && !wide && s->world_node_count > 0 && s->world_depth <= rtx::kShortStack) {
+        t2_threads = c->trace_threads >= 1024 ? 1024 : c->trace_threads >= 896 ? 896 : (c->trace_threads >= 640 ? 640 : (c->trace_threads >= 512 ? 512 : 448));
+        const size_t stack_bytes = (size_t)(1 + rtx::kShortStack) * (size_t)t2_threads * 4 + 16;
+        const size_t room = (size_t)c->smem_optin > stack_bytes ? (size_t)c->smem_optin - stack_bytes : 0;
+        int cap = (int)std::min<size_t>(room / 64, (size_t)s->world_node_count);
+        if (cap < 1) {
+            t2_threads = 0;
+        } else {
+            tcfg.stage_first = s->world_first_node;
+            tcfg.n_stage = cap;
+            tcfg.cap = cap;
+            tcfg.t_leaf = c->t_leaf; tcfg.t_refill = c->t_refill; tcfg.burst = c->t_burst;
+            t2_smem = (size_t)cap * 64 + stack_bytes;
+        }
+    }
+    const bool t2_all = t2_threads != 0 && tcfg.n_stage == s->world_node_count;
+    auto launch_trace2 = [&](const Part& pt) -> cudaError_t {
+        // one CTA per SM (fewer when the partition is small): each stages the BVH once and walks its share of the slots
+        unsigned grid = std::min<unsigned>(t2_grid_cap, (unsigned)((pt.a.n_slots + t2_threads - 1) / t2_threads));
+        if (grid < 1) grid = 1;
+#define RTX_T2_LAUNCH(CNT, THR, ALL)                                                                                              \
+    do {                                                                                                                          \
+        auto k = rtx::wf_trace2_kernel<CNT, THR, ALL>;                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem);                        \
+        if (e != cudaSuccess) return e;                                                                                           \
+        k<<<grid, THR, t2_smem, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, tcfg, d_ray_count, CNT ? c->d_counters : nullptr); \
+    } while (0)
+#define RTX_T2_THREADS(CNT, ALL)                                  \
+    do {                                                          \
+        if (t2_threads == 1024) RTX_T2_LAUNCH(CNT, 1024, ALL);    \
+        else if (t2_threads == 896) RTX_T2_LAUNCH(CNT, 896, ALL); \
+        else if (t2_threads == 640) RTX_T2_LAUNCH(CNT, 640, ALL); \
+        else if (t2_threads == 512) RTX_T2_LAUNCH(CNT, 512, ALL); \
+        else RTX_T2_LAUNCH(CNT, 448, ALL);                        \
+    } while (0)
+        if (counted) { if (t2_all) RTX_T2_THREADS(true, true); else RTX_T2_THREADS(true, false); }
+        else { if (t2_all) RTX_T2_THREADS(false, true); else RTX_T2_THREADS(false, false); }
+#undef RTX_T2_THREADS
+#undef RTX_T2_LAUNCH
+        return cudaSuccess;
+    };
     size_t prof_used = 0;
     // every kProfStride-th iteration of partition 0 is bracketed (events between back-to-back launches cost ~10 %
     // when every launch has them); the accumulated times are scaled back up by the stride
@@ -671,7 +737,13 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 }
                 prof_now = q == 0 && c->profiling && (iteration++ % kProfStride) == 0;
                 CU(prof_mark());
-                if (counted) {
+                if (t2_threads != 0) {
+                    if (counted) rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                    else rtx::wf_shade_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
+                    CU(prof_mark());
+                    CU(prof_mark());
+                    CU(launch_trace2(pt));
+                } else if (counted) {
                     rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
                     CU(prof_mark());
                     CU(prof_mark());

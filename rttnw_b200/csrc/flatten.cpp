@@ -603,8 +603,14 @@ struct Flattener {
             }
         } else {
             BvhBuilder b(out.nodes, out.records, w.items);
+            const size_t first_node = out.nodes.size();
             root = b.build(bounds);
             out.max_stack = std::max(out.max_stack, 1 + b.depth + 1);
+            if (!w.is_boundary) {
+                out.world_first_node = (int32_t)first_node;
+                out.world_node_count = (int32_t)(out.nodes.size() - first_node);
+                out.world_depth = b.depth;
+            }
             if (wide_copy && !w.is_boundary && b.root_tmp >= 0) {  // the 4-wide copy of the world BVH (opt-in traversal, RTX_BVH_WIDE)
                 const int32_t wide = b.emit_wide(b.root_tmp);
                 if (1 + 3 * b.wide_depth + 1 <= kTraversalStack) out.wide_root = wide;  // up to three siblings deferred per level

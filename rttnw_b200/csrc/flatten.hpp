@@ -36,6 +36,9 @@ struct FlatScene {
     int32_t world_first_record = 0, world_count = 0;
     std::vector<float> world_boxes;
     int32_t world_root = 0;
+    // the world BVH's nodes are nodes[world_first_node, + world_node_count), root first; world_depth = inner nodes on
+    // its longest root-to-leaf path (the shared-memory traversal stages that range and needs one stack entry per level)
+    int32_t world_first_node = 0, world_node_count = 0, world_depth = 0;
     int32_t wide_root = -1;      // the same BVH 4-wide (two consecutive BvhNode entries per node), -1: not built
     int32_t n_media = 0;
     int32_t n_prims = 0;  // number of primitive ids handed out

@@ -201,14 +201,29 @@ def test_fixed_rays_random_scene_trees(ctx, seed):
 TEN_MILLION = {  # scene: (instanced-geometry id range whose p is Q14-displaced, or None)
     1: None, 2: None, 3: None, 4: None, 5: None, 6: None, 7: (6, 18), 8: (6, 20), 9: (2411, 3411),
 }
+# Largest share of rays the oracle may flag as grazing ties (a comparison of the reference within 1e-9 relative of
+# flipping, for a candidate at or before the final hit), per scene: twice what the 10^7-ray run of round 2 observed
+# (profiles/r2_parity.json), floored at 1e-4. Scene 9's secondary rays travel inside the ground boxes and meet the
+# exactly coplanar side faces adjacent boxes share (scenes.rs:244-253): genuine two-primitive ties.
+MAX_TIE_SHARE = {1: 1e-4, 2: 1e-4, 3: 1e-4, 4: 1e-4, 5: 1e-4, 6: 2e-3, 7: 4e-3, 8: 2e-3, 9: 3.5e-2}
+
+
+def trace_on_device(gsc, rays):
+    import torch
+    n = rays.shape[0]
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(n * 88, dtype=torch.uint8, device="cuda")
+    gsc.trace_device(d_rays, d_hits, n)
+    return d_hits.cpu().numpy().view(abi.HIT_DTYPE)
 
 
 @pytest.mark.parametrize("number", sorted(TEN_MILLION))
 def test_ten_million_fixed_rays(ctx, number, earth_rgba):
-    """BASELINE.json's size: 10^7 fixed rays per scene (half camera rays, half secondary rays leaving the
-    surfaces the first half hit), resident on the device. Checked through size-independent properties
-    plus a 10^5 subsample of the secondary set against the oracle."""
-    import torch
+    """BASELINE.json's size and contract: 10^7 fixed rays per scene (half camera rays, half secondary rays leaving
+    the surfaces the first half hit), EVERY ONE compared with the oracle's hit() — primitive id bit-exact outside
+    grazing ties, t / p / normal / u / v within 1e-5 relative — plus two size-independent properties of the answers
+    (p = o + t d, and nothing closer than the reported hit). The counts and the largest errors go to r2_parity.json."""
+    from tests._record import record
     n = 10_000_000
     rng = np.random.default_rng(0xF17ED + number)
     gsc = R.DeviceScene(ctx, R.BuiltinDesc(number))
@@ -216,28 +231,15 @@ def test_ten_million_fixed_rays(ctx, number, earth_rgba):
     n_prims = osc.prim_count
     cam, _ = osc.camera()
     half = n // 2
-    primary = RY.camera_rays(cam, half, rng)
-    d_rays = torch.from_numpy(primary.view(np.uint8).reshape(-1)).cuda()
-    d_hits = torch.empty(half * 88, dtype=torch.uint8, device="cuda")
-    gsc.trace_device(d_rays, d_hits, half)
-    h1 = d_hits.cpu().numpy().view(abi.HIT_DTYPE)
-    del d_rays, d_hits
-    # the second half: secondary rays, recycled until there are `half` of them
-    secondary = RY.secondary_rays(h1, primary, rng)
-    assert secondary.shape[0] > 0.3 * half
-    reps = -(-half // secondary.shape[0])
-    if reps > 1:
-        secondary = np.concatenate([secondary] + [RY.secondary_rays(h1, primary, rng) for _ in range(reps - 1)])
-    secondary = secondary[:half]
-    m = secondary.shape[0]
-    assert m + half == n
-    d_rays2 = torch.from_numpy(secondary.view(np.uint8).reshape(-1)).cuda()
-    d_hits2 = torch.empty(m * 88, dtype=torch.uint8, device="cuda")
-    gsc.trace_device(d_rays2, d_hits2, m)
-    h2 = d_hits2.cpu().numpy().view(abi.HIT_DTYPE)
-    del d_rays2, d_hits2
+    chunk = 2_500_000
     displaced = TEN_MILLION[number]
-    for rays, hits in ((primary, h1), (secondary, h2)):
+    stats = {"primary": None, "secondary": None}
+    seeds_for_secondary = []
+
+    def check_chunk(kind, rays):
+        hits = trace_on_device(gsc, rays)
+        ref, fragile = osc.trace(rays)
+        stats[kind] = RY.merge_stats(stats[kind], RY.compare_hits(hits, ref, fragile))
         hit = hits["prim_id"] >= 0
         assert ((hits["prim_id"] >= -1) & (hits["prim_id"] < n_prims)).all()
         assert (hits["t"][hit] >= 0.001).all() and np.isfinite(hits["t"][hit]).all()
@@ -247,16 +249,34 @@ def test_ten_million_fixed_rays(ctx, number, earth_rgba):
         assert np.allclose(p[plain], hits["p"][plain], rtol=1e-9, atol=1e-6)
         # idempotence: nothing is closer than the reported hit (media aside: their hit is a draw)
         cand = np.nonzero(hit & (hits["material"] >= 0))[0]
-        sub = rng.choice(cand, min(200000, cand.shape[0]), replace=False)
+        sub = rng.choice(cand, min(100000, cand.shape[0]), replace=False)
         again = rays[sub].copy()
         again["t_max"] = hits["t"][sub] * (1 - 1e-9)
         again["xi"] = 1e-300  # an (essentially) infinite free flight: media never scatter
-        res = gsc.trace(again)
-        assert (res["prim_id"] == abi.RTX_MISS).mean() > 0.9999
-    sub = rng.choice(m, 100000, replace=False)
-    ref, fragile = osc.trace(secondary[sub])
-    st = RY.compare_hits(h2[sub], ref, fragile)
-    assert st["fragile"] < 0.06 * st["rays"], st
+        assert (gsc.trace(again)["prim_id"] == abi.RTX_MISS).mean() > 0.9999
+        return hits
+
+    for _ in range(half // chunk):
+        primary = RY.camera_rays(cam, chunk, rng)
+        h1 = check_chunk("primary", primary)
+        seeds_for_secondary.append((h1, primary))
+    # the second half: secondary rays off the first half's hits, recycled until there are `half` of them
+    done = 0
+    k = 0
+    while done < half:
+        h1, primary = seeds_for_secondary[k % len(seeds_for_secondary)]
+        k += 1
+        secondary = RY.secondary_rays(h1, primary, rng)[:min(chunk, half - done)]
+        assert secondary.shape[0] > 0
+        check_chunk("secondary", secondary)
+        done += secondary.shape[0]
+    total = RY.merge_stats(stats["primary"], stats["secondary"])
+    assert total["rays"] == n
+    entry = {"rays": n, "primary": stats["primary"], "secondary": stats["secondary"],
+             "tie_share": total["fragile"] / n, "max_tie_share_allowed": MAX_TIE_SHARE[number]}
+    record("fixed_rays_10M", f"scene_{number}", entry)
+    print(f"scene {number}: {entry}")
+    assert total["fragile"] <= MAX_TIE_SHARE[number] * n, entry
 
 
 # ---------------------------------------------------------------------------
