@@ -15,7 +15,9 @@
 #include "flatten.hpp"
 #include "kernels.cuh"
 #include "lbvh.cuh"
+#include "shade2.cuh"
 #include "trace2.cuh"
+#include "trace3.cuh"
 #include "scene_api.hpp"
 
 namespace {
@@ -80,12 +82,19 @@ struct rtx_ctx {
     int wf_batch = 8;
     int wf_wide = 0;     // RTX_BVH_WIDE=1: the trace kernel walks the 4-wide copy of the world BVH (measured slower: DESIGN.md §4)
     int wf_streams = 2;  // pool partitions driven concurrently on their own streams (RTX_WF_STREAMS, at most 4)
-    // trace kernel form (RTX_TRACE): 2 = world BVH + stacks in shared memory, persistent warps (trace2.cuh), used when the
-    // BVH is shallow enough for the shared stack; 1 = the first form (wf_trace_kernel), always available
-    int trace_form = 2;
+    // trace kernel form (RTX_TRACE). 1 (default): one slot per thread, while-while, local-memory stack (wf_trace_kernel).
+    // The others were built in round 2 to test what ncu pointed at, measured on scene 9 against 604 M samples/s for
+    // form 1 and kept as opt-in, parity-tested variants (DESIGN.md §4 has the numbers): 2 = world BVH + stacks in shared
+    // memory, persistent warps with voted refill (trace2.cuh; 543-572 M); 3 = rays regrouped by kind of work through
+    // shared memory every few steps (trace3.cuh; 238-342 M); 4 = form 1 with a shared-memory stack and 32-byte node
+    // loads (trace2.cuh, "1c"; 596 M). Forms 2-4 need a world BVH no deeper than kShortStack and fall back to 1.
+    int trace_form = 1;
     int trace_threads = 896;               // CTA size of the shared-memory form, one CTA per SM (RTX_TRACE_THREADS: 896, 640, 512, 448)
     int t_leaf = 33, t_refill = 33, t_burst = 1 << 30;  // its vote thresholds (RTX_T_LEAF / RTX_T_REFILL / RTX_T_BURST)
     int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    int prof_stride = 8;                   // RTX_PROF_STRIDE: every n-th iteration of partition 0 is bracketed when profiling is on
+    bool debug_batches = false;            // RTX_DEBUG_BATCHES=1: one stderr line per batch and partition
+    int shade_form = 2;                    // RTX_SHADE: 2 = media after the surface search + early dispenser request (shade2.cuh), 1 = first form
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> join_events;
     cudaEvent_t fork_event = nullptr;
@@ -167,6 +176,9 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->t_leaf = env_int("RTX_T_LEAF", c->t_leaf);
     c->t_refill = env_int("RTX_T_REFILL", c->t_refill);
     c->t_burst = env_int("RTX_T_BURST", c->t_burst);
+    c->shade_form = env_int("RTX_SHADE", c->shade_form);
+    c->debug_batches = env_int("RTX_DEBUG_BATCHES", 0) != 0;
+    c->prof_stride = env_int("RTX_PROF_STRIDE", c->prof_stride);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
     if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : 0;
@@ -669,7 +681,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
         t2_threads = c->trace_threads >= 1024 ? 1024 : c->trace_threads >= 896 ? 896 : (c->trace_threads >= 640 ? 640 : (c->trace_threads >= 512 ? 512 : 448));
         const size_t stack_bytes = (size_t)(1 + rtx::kShortStack) * (size_t)t2_threads * 4 + 16;
         const size_t room = (size_t)c->smem_optin > stack_bytes ? (size_t)c->smem_optin - stack_bytes : 0;
-        int cap = (int)std::min<size_t>(room / 64, (size_t)s->world_node_count);
+        int cap = (int)std::min<size_t>(room / rtx::kNodeStride, (size_t)s->world_node_count);
         if (cap < 1) {
             t2_threads = 0;
         } else {
@@ -677,9 +689,56 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             tcfg.n_stage = cap;
             tcfg.cap = cap;
             tcfg.t_leaf = c->t_leaf; tcfg.t_refill = c->t_refill; tcfg.burst = c->t_burst;
-            t2_smem = (size_t)cap * 64 + stack_bytes;
+            t2_smem = (size_t)cap * rtx::kNodeStride + stack_bytes;
         }
     }
+    // sorted form (RTX_TRACE=3): rays regrouped by the kind of work they need next, through shared memory (trace3.cuh)
+    rtx::Trace3Cfg t3cfg{};
+    int t3_threads = 0;
+    size_t t3_smem = 0;
+    if (c->trace_form == 3 && !wide && s->world_node_count > 0 && s->world_depth <= rtx::kShortStack) {
+        t3_threads = c->trace_threads >= 896 ? 896 : (c->trace_threads >= 768 ? 768 : (c->trace_threads >= 640 ? 640 : 512));
+        const size_t fixed = rtx::trace3_smem_bytes(t3_threads, 0);
+        const size_t room = (size_t)c->smem_optin > fixed ? (size_t)c->smem_optin - fixed : 0;
+        const int cap = (int)std::min<size_t>(room / rtx::kNodeStride, (size_t)s->world_node_count);
+        if (cap < 1) {
+            t3_threads = 0;
+        } else {
+            t3cfg.stage_first = s->world_first_node;
+            t3cfg.n_stage = cap;
+            t3cfg.cap = cap;
+            t3cfg.burst = c->t_burst > 64 ? 4 : c->t_burst;
+            t3_smem = rtx::trace3_smem_bytes(t3_threads, cap);
+            t2_threads = 0;
+        }
+    }
+    // form "1c" (RTX_TRACE=4): the first form's launch shape with the stack in shared memory and 32-byte node loads
+    const bool t1c = c->trace_form == 4 && !wide && s->world_depth <= rtx::kShortStack;
+    if (t1c) t2_threads = 0;
+    const bool t3_all = t3_threads != 0 && t3cfg.n_stage == s->world_node_count;
+    auto launch_trace3 = [&](const Part& pt) -> cudaError_t {
+        unsigned grid = std::min<unsigned>((unsigned)c->sm_count, (unsigned)((pt.a.n_slots + t3_threads - 1) / t3_threads));
+        if (grid < 1) grid = 1;
+#define RTX_T3_LAUNCH(CNT, THR, ALL)                                                                                               \
+    do {                                                                                                                           \
+        auto k = rtx::wf_trace3_kernel<CNT, THR, ALL>;                                                                             \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3_smem);                         \
+        if (e != cudaSuccess) return e;                                                                                            \
+        k<<<grid, THR, t3_smem, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, t3cfg, d_ray_count, CNT ? c->d_counters : nullptr); \
+    } while (0)
+#define RTX_T3_THREADS(CNT, ALL)                                  \
+    do {                                                          \
+        if (t3_threads == 896) RTX_T3_LAUNCH(CNT, 896, ALL);      \
+        else if (t3_threads == 768) RTX_T3_LAUNCH(CNT, 768, ALL); \
+        else if (t3_threads == 640) RTX_T3_LAUNCH(CNT, 640, ALL); \
+        else RTX_T3_LAUNCH(CNT, 512, ALL);                        \
+    } while (0)
+        if (counted) { if (t3_all) RTX_T3_THREADS(true, true); else RTX_T3_THREADS(true, false); }
+        else { if (t3_all) RTX_T3_THREADS(false, true); else RTX_T3_THREADS(false, false); }
+#undef RTX_T3_THREADS
+#undef RTX_T3_LAUNCH
+        return cudaSuccess;
+    };
     const bool t2_all = t2_threads != 0 && tcfg.n_stage == s->world_node_count;
     auto launch_trace2 = [&](const Part& pt) -> cudaError_t {
         // one CTA per SM (fewer when the partition is small): each stages the BVH once and walks its share of the slots
@@ -709,7 +768,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     size_t prof_used = 0;
     // every kProfStride-th iteration of partition 0 is bracketed (events between back-to-back launches cost ~10 %
     // when every launch has them); the accumulated times are scaled back up by the stride
-    constexpr int kProfStride = 8;
+    const int kProfStride = c->prof_stride;
     long long iteration = 0;
     bool prof_now = false;
     auto prof_mark = [&](void) -> cudaError_t {
@@ -737,24 +796,28 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 }
                 prof_now = q == 0 && c->profiling && (iteration++ % kProfStride) == 0;
                 CU(prof_mark());
-                if (t2_threads != 0) {
+                if (c->shade_form >= 2) {
+                    if (counted) rtx::wf_shade2_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                    else rtx::wf_shade2_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
+                } else {
                     if (counted) rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
                     else rtx::wf_shade_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
-                    CU(prof_mark());
-                    CU(prof_mark());
+                }
+                CU(prof_mark());
+                CU(prof_mark());
+                if (t1c) {
+                    if (counted) rtx::wf_trace1c_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
+                    else rtx::wf_trace1c_kernel<false><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
+                } else if (t3_threads != 0) {
+                    CU(launch_trace3(pt));
+                } else if (t2_threads != 0) {
                     CU(launch_trace2(pt));
                 } else if (counted) {
-                    rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
-                    CU(prof_mark());
-                    CU(prof_mark());
                     if (wide)
                         rtx::wf_trace_kernel<true, true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
                     else
                         rtx::wf_trace_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
                 } else {
-                    rtx::wf_shade_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
-                    CU(prof_mark());
-                    CU(prof_mark());
                     if (wide)
                         rtx::wf_trace_kernel<false, true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
                     else
@@ -779,6 +842,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 if (pt.done) continue;
                 CU(cudaEventSynchronize(c->batch_done[2 * q + prev]));
                 const unsigned long long* hs = c->h_status + 4 * q + 2 * prev;
+                if (c->debug_batches) std::fprintf(stderr, "[rtx] batch %d partition %d: %u rays written by its last shade pass, dispenser at %llu of %llu\n", k - 1, q, (unsigned int)hs[0], hs[1], total);
                 if ((unsigned int)hs[0] == 0 && hs[1] >= total) { pt.done = true; --remaining; }
             }
         }

@@ -100,9 +100,14 @@ struct alignas(16) DMedium {
     float lo[3];
     int32_t record;  // index of the REC_MEDIUM record
     float hi[3];
-    int32_t _pad;
+    int32_t ordinal;  // which Philox MEDIUM word this medium draws (the record's d[1], as an integer)
+    // 1 / density rounded toward zero: a LOWER bound of the distance -ln(u) / density the medium lets a ray fly
+    // (hittable.rs:765), for the fp32 filter that skips the f64 boundary test when the ray cannot scatter in front of
+    // the surface it already hit
+    float inv_density_lb;
+    int32_t _pad[3];
 };
-static_assert(sizeof(DMedium) == 32, "DMedium must be 32 bytes");
+static_assert(sizeof(DMedium) == 48, "DMedium must be 48 bytes");
 
 struct DImage {
     unsigned long long tex;  // cudaTextureObject_t (0: failed load -> cyan)

@@ -622,6 +622,12 @@ struct Flattener {
             std::memset(&dm, 0, sizeof(dm));
             for (int i = 0; i < 3; ++i) { dm.lo[i] = round_down(m.box.lo[i]); dm.hi[i] = round_up(m.box.hi[i]); }
             dm.record = (int32_t)out.records.size();
+            dm.ordinal = (int32_t)m.rec.d[1];
+            {
+                float lb = (float)std::fabs(m.rec.d[0]);  // |-1 / density|
+                if ((double)lb > std::fabs(m.rec.d[0])) lb = std::nextafterf(lb, 0.f);
+                dm.inv_density_lb = lb;
+            }
             out.records.push_back(m.rec);
             out.media.push_back(dm);
             bounds.grow(m.box);

@@ -43,29 +43,48 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+constexpr uint32_t kNodeStride = 80;  // bytes between staged nodes: 64 of data + 16 of padding, so that chunk c of node i starts in
+                                      // 16-byte bank group (5 i + c) mod 8 — lanes in different nodes spread over the banks
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds64i(uint32_t addr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds32i(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32i(uint32_t addr, int32_t v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v)); }
+
 // One inner node from the staged copy (or, past the staged range, from global memory): both child boxes against
 // the ray; returns the next node and defers the farther child when both are hit. Node references are relative to
-// the first staged node. `top` is the top of the stack (in a register), `sp` points at the first free shared entry
-// of this thread's column (stride kThreads entries).
+// the first staged node. `top` is the top of the stack (in a register), `sp` the shared-window address of the first
+// free entry of this thread's column (stride kThreads entries). Shared memory is addressed through 32-bit window
+// addresses: with generic pointers ptxas rebuilt the window base (S2UR + two uniform ops) in every trip of the loop.
 template <int kThreads, bool kAllStaged, bool kCount>
-__device__ __forceinline__ int32_t node_step2(const uint4* __restrict__ s_nodes, const TraceCfg& cfg, const BvhNode* __restrict__ g_nodes,
-                                              int32_t cur, const SlabRay& s, float tmin_f, float tmax_f, int32_t& top, int32_t*& sp,
+__device__ __forceinline__ int32_t node_step2(uint32_t s_nodes, const TraceCfg& cfg, const BvhNode* __restrict__ g_nodes,
+                                              int32_t cur, const SlabRay& s, float tmin_f, float tmax_f, int32_t& top, uint32_t& sp,
                                               Tally<kCount>& tally) {
     float4 q0, q1, q2;
-    int4 meta;
+    int2 meta;
     if (kAllStaged || cur < cfg.n_stage) {
-        const uint4* p = s_nodes + cur;
-        uint4 a = p[0], b = p[cfg.cap], c = p[2 * cfg.cap], d = p[3 * cfg.cap];
-        q0 = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-        q1 = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
-        q2 = make_float4(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), __uint_as_float(c.w));
-        meta = make_int4((int)d.x, (int)d.y, 0, 0);
+        const uint32_t p = s_nodes + (uint32_t)cur * kNodeStride;
+        q0 = lds128(p);
+        q1 = lds128(p + 16);
+        q2 = lds128(p + 32);
+        meta = lds64i(p + 48);
     } else {
         const float4* np = reinterpret_cast<const float4*>(g_nodes + cur);
         q0 = __ldg(np); q1 = __ldg(np + 1); q2 = __ldg(np + 2);
-        meta = __ldg(reinterpret_cast<const int4*>(np + 3));
-        if (meta.x >= 0) meta.x -= cfg.stage_first;
-        if (meta.y >= 0) meta.y -= cfg.stage_first;
+        const int4 mt = __ldg(reinterpret_cast<const int4*>(np + 3));
+        meta = make_int2(mt.x >= 0 ? mt.x - cfg.stage_first : mt.x, mt.y >= 0 ? mt.y - cfg.stage_first : mt.y);
     }
     tally.node();
     float n0, n1;
@@ -73,16 +92,16 @@ __device__ __forceinline__ int32_t node_step2(const uint4* __restrict__ s_nodes,
     const bool h1 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, n1);
     if (h0 && h1) {
         const bool swap = n1 < n0;
-        *sp = top;
-        sp += kThreads;
+        sts32i(sp, top);
+        sp += kThreads * 4;
         top = swap ? meta.x : meta.y;
         return swap ? meta.y : meta.x;
     }
     if (h0) return meta.x;
     if (h1) return meta.y;
     const int32_t r = top;
-    sp -= kThreads;
-    top = *sp;  // (below the first entry lies the pad row: a finished ray pops it once, nobody looks at the value)
+    sp -= kThreads * 4;
+    top = lds32i(sp);  // (below the first entry lies the pad row: a finished ray pops it once, nobody looks at the value)
     return r;
 }
 
@@ -92,12 +111,13 @@ __global__ void __launch_bounds__(kThreads, 1) wf_trace2_kernel(SceneView sc, Pa
     extern __shared__ __align__(16) unsigned char tr_smem[];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
-    uint4* s_nodes = reinterpret_cast<uint4*>(tr_smem);
-    int32_t* s_stack = reinterpret_cast<int32_t*>(s_nodes + 4 * (size_t)cfg.cap);  // [1 + kShortStack][kThreads], row 0 = pad
-    int* s_next = reinterpret_cast<int*>(s_stack + (1 + kShortStack) * kThreads);
+    // layout: staged nodes (kNodeStride bytes each) | stack [1 + kShortStack][kThreads] int32, row 0 = pad | counter
+    const uint32_t s_nodes = (uint32_t)__cvta_generic_to_shared(tr_smem);
+    const uint32_t s_stack = s_nodes + (uint32_t)cfg.cap * kNodeStride;
+    int* s_next = reinterpret_cast<int*>(tr_smem + (size_t)cfg.cap * kNodeStride + (size_t)(1 + kShortStack) * kThreads * 4);
     Tally<kCount> tally;
 
-    // ---- stage the top of the world BVH: four planes of 16-byte chunks, child references made relative ----
+    // ---- stage the top of the world BVH, child references made relative to its first node ----
     {
         const uint4* g = reinterpret_cast<const uint4*>(sc.nodes + cfg.stage_first);
         const int n_chunks = 4 * cfg.n_stage;
@@ -108,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) wf_trace2_kernel(SceneView sc, Pa
                 if ((int32_t)v.x >= 0) v.x -= (uint32_t)cfg.stage_first;
                 if ((int32_t)v.y >= 0) v.y -= (uint32_t)cfg.stage_first;
             }
-            s_nodes[(size_t)c * cfg.cap + n] = v;
+            *reinterpret_cast<uint4*>(tr_smem + (size_t)n * kNodeStride + (size_t)c * 16) = v;
         }
     }
     // this CTA's share of the pool: every gridDim.x-th piece of 32 slots (neighbouring slots hold rays of similar cost —
@@ -120,14 +140,14 @@ __global__ void __launch_bounds__(kThreads, 1) wf_trace2_kernel(SceneView sc, Pa
 
     const BvhNode* g_nodes = sc.nodes + cfg.stage_first;
     const int32_t root = sc.world_root - cfg.stage_first;
-    int32_t* const sp0 = s_stack + kThreads + tid;  // first entry of this thread's column
+    const uint32_t sp0 = s_stack + (uint32_t)(kThreads + tid) * 4;  // first entry of this thread's column
     const float tmin_f = __int_as_float(0x3a83126e);  // the largest float below 0.001 (main.rs:36's t_min, rounded down)
     const uint32_t lt = lanemask_lt();
 
     // lane state
     int32_t cur = kSentinel;  // >= 0: inner node; < 0: leaf code; kSentinel: idle
     int32_t top = kSentinel;
-    int32_t* sp = sp0;
+    uint32_t sp = sp0;
     int slot = -1;
     RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
     SlabRay sr{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -146,8 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) wf_trace2_kernel(SceneView sc, Pa
                 const int32_t v = ~cur;
                 const int32_t first = v >> 4, count = v & 15;
                 cur = top;
-                sp -= kThreads;
-                top = *sp;
+                sp -= kThreads * 4;
+                top = lds32i(sp);
                 for (int32_t i = 0; i < count; ++i) {
                     const int4 h = __ldg(reinterpret_cast<const int4*>(sc.records + first + i));
                     double t;
@@ -194,10 +214,10 @@ __global__ void __launch_bounds__(kThreads, 1) wf_trace2_kernel(SceneView sc, Pa
             if (((((base + __popc(m)) >> 5) * G + b) << 5) >= n_slots) dry = true;
         } else if (nn > 0) {
             // ================= node phase: up to `burst` steps for every lane that has a node =================
-#pragma unroll 1
-            for (int it = 0; it < cfg.burst; ++it) {
-                if (cur >= 0) cur = node_step2<kThreads, kAllStaged>(s_nodes, cfg, g_nodes, cur, sr, tmin_f, tmax_f, top, sp, tally);
-                if (!__any_sync(FULL, cur >= 0)) break;
+            int left = cfg.burst;
+            while (cur >= 0 && left > 0) {  // (a per-lane loop: a vote per step cost 7 instructions and 13 % of the stall samples)
+                --left;
+                cur = node_step2<kThreads, kAllStaged>(s_nodes, cfg, g_nodes, cur, sr, tmin_f, tmax_f, top, sp, tally);
             }
         } else {
             break;  // dry, and no ray in flight
@@ -211,6 +231,112 @@ __global__ void __launch_bounds__(kThreads, 1) wf_trace2_kernel(SceneView sc, Pa
     if (ray_count) {
         for (int off = 16; off > 0; off >>= 1) my_rays += __shfl_xor_sync(FULL, my_rays, off);
         if (lane == 0 && my_rays) atomicAdd(ray_count, (unsigned long long)my_rays);
+    }
+    if constexpr (kCount) {
+        uint32_t vals[3] = {tally.n_node, tally.n_sphere, tally.n_rect};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            for (int off = 16; off > 0; off >>= 1) vals[k] += __shfl_xor_sync(FULL, vals[k], off);
+        if (lane == 0) {
+            atomicAdd(&counters->node_visits, (unsigned long long)vals[0]);
+            atomicAdd(&counters->box_tests, 2ull * vals[0]);
+            atomicAdd(&counters->sphere_tests, (unsigned long long)vals[1]);
+            atomicAdd(&counters->rect_tests, (unsigned long long)vals[2]);
+        }
+    }
+}
+
+}  // namespace rtx
+
+namespace rtx {
+
+// ---------------------------------------------------------------------------
+// K2b, form "1c": the launch shape of the first form (one slot per thread, 128-thread CTAs, nothing persistent, so the
+// other partition's shade CTAs interleave with these on every SM) with the two things the ncu source view of the first
+// form shows its warps waiting for taken off the critical path: the stack is a shared-memory column with its top in a
+// register (the pop that follows a miss was 11.6 % of all stall samples as a local-memory load; local stack traffic
+// used 2.2-2.5 of the 32 bytes of each sector it moved), and a node is two 32-byte loads instead of four 16-byte ones
+// (one L1 wavefront per lane per load instruction: the L1 data pipe was the busiest unit at 64 %).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(kTraceBlock, WF_TRACE_MINB*(128 / kTraceBlock)) wf_trace1c_kernel(SceneView sc, PathPool pool, int n_slots,
+                                                                                                    unsigned long long* ray_count, Counters* counters) {
+    __shared__ int32_t s_stack[(1 + kShortStack) * kTraceBlock];  // row 0 = pad (a finished ray pops it once)
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int i = blockIdx.x * kTraceBlock + tid;
+    Tally<kCount> tally;
+    const bool act = i < n_slots && pool.bounce[i] >= 0;
+    if (act) {
+        const RayD ray{mk(pool.ox[i], pool.oy[i], pool.oz[i]), mk(pool.dx[i], pool.dy[i], pool.dz[i]), pool.time[i]};
+        Best best{pool.best_t[i], -1, 0};
+        SlabRay s;
+        make_slab(ray.o, ray.d, s);
+        const float tmin_f = __int_as_float(0x3a83126e);  // the largest float below 0.001
+        float tmax_f = __double2float_ru(best.t);
+        int32_t top = kSentinel;
+        uint32_t sp = (uint32_t)__cvta_generic_to_shared(s_stack) + (uint32_t)(kTraceBlock + tid) * 4;
+        int32_t cur = sc.world_root;
+        while (true) {
+            while (cur >= 0) {
+                const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+                float4 q0, q1, q2, q3;
+                ldg256(np, q0, q1);
+                ldg256(np + 2, q2, q3);
+                tally.node();
+                float n0, n1;
+                const bool h0 = slab(s, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, tmin_f, tmax_f, n0);
+                const bool h1 = slab(s, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, tmin_f, tmax_f, n1);
+                const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                if (h0 && h1) {
+                    const bool swap = n1 < n0;
+                    sts32i(sp, top);
+                    sp += kTraceBlock * 4;
+                    top = swap ? c0 : c1;
+                    cur = swap ? c1 : c0;
+                } else if (h0) {
+                    cur = c0;
+                } else if (h1) {
+                    cur = c1;
+                } else {
+                    cur = top;
+                    sp -= kTraceBlock * 4;
+                    top = lds32i(sp);
+                }
+            }
+            if (cur == kSentinel) break;
+            const int32_t v = ~cur;
+            const int32_t first = v >> 4, count = v & 15;
+            cur = top;
+            sp -= kTraceBlock * 4;
+            top = lds32i(sp);
+            for (int32_t k = 0; k < count; ++k) {
+                const int4 h = __ldg(reinterpret_cast<const int4*>(sc.records + first + k));
+                double t;
+                int32_t hit_rec;
+                if (test_geometry(sc, first + k, h, ray, 0.001, best.t, t, hit_rec, tally)) {
+                    best.t = t;
+                    best.rec = hit_rec;
+                    best.chain = h.w;
+                    tmax_f = __double2float_ru(t);
+                }
+            }
+        }
+        if (best.rec >= 0) {  // closer than the medium candidate (if any) the shade kernel left there
+            pool.best_t[i] = best.t;
+            pool.best_rec[i] = best.rec;
+            pool.best_chain[i] = best.chain;
+        }
+    }
+    if (ray_count) {
+        const unsigned am = __ballot_sync(FULL, act);
+        if (lane == 0 && am != 0) atomicAdd(ray_count, (unsigned long long)__popc(am));
     }
     if constexpr (kCount) {
         uint32_t vals[3] = {tally.n_node, tally.n_sphere, tally.n_rect};

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--lib", default=None)
+    ap.add_argument("--warm", type=int, default=0, help="spp of the warm-up render (default spp / 4, at least 8)")
+    ap.add_argument("--counted", action="store_true", help="also run the counting build once and print the per-ray means")
     ap.add_argument("--prof", action="store_true", help="bracket every 8th iteration with CUDA events (costs ~1-2 %)")
     ap.add_argument("configs", nargs="*")
     args = ap.parse_args()
@@ -66,7 +68,7 @@ def main():
             abi.check(lib.rtx_render(ctx, sc, C.byref(p), acc, rays))
             abi.check(lib.rtx_ctx_sync(ctx))
             return time.perf_counter() - t0
-        render(0, max(8, args.spp // 4))
+        render(0, args.warm or max(8, args.spp // 4))
         if args.prof:
             abi.check(lib.rtx_ctx_set_profiling(ctx, 1))
         ts = sorted(render(k + 1, args.spp) for k in range(args.reps))
@@ -77,10 +79,19 @@ def main():
         abi.check(lib.rtx_memcpy_d2h(ctx, nr.ctypes.data, rays, 8))
         mean = (host[..., :3].sum(axis=(0, 1)) / host[..., 3].sum()).tolist()
         it = max(1, n.value)
+        nl = C.c_uint64()
+        abi.check(lib.rtx_ctx_kernel_launches(ctx, C.byref(nl)))
         best, med = n_px * args.spp / ts[0] / 1e6, n_px * args.spp / ts[len(ts) // 2] / 1e6
-        prof = f" shade {1e3 * a.value / it:6.1f} us trace {1e3 * b.value / it:6.1f} us/launch" if args.prof else ""
+        prof = (f" shade {1e3 * a.value / it:6.1f} us trace {1e3 * b.value / it:6.1f} us/launch (kernels {a.value + b.value:.1f} ms of "
+                f"{1e3 * sum(ts):.1f} ms wall)") if args.prof else ""
         print(f"{cfg or '(default)':60s} | best {best:7.1f} med {med:7.1f} Msamples/s  {float(nr[0]) / (n_px * args.spp):.3f} rays/sample{prof}"
-              f"  mean rgb {mean[0]:.5f} {mean[1]:.5f} {mean[2]:.5f}", flush=True)
+              f"  mean rgb {mean[0]:.5f} {mean[1]:.5f} {mean[2]:.5f}  launches {nl.value}", flush=True)
+        if args.counted:
+            st = abi.TraceStats()
+            abi.check(lib.rtx_memset_zero(ctx, acc, n_px * 16))
+            p = abi.RenderParams(w, h, 0, 4, d["max_depth"], 0, 1)
+            abi.check(lib.rtx_render_counted(ctx, sc, C.byref(p), acc, C.byref(st)))
+            print("    per ray: " + "  ".join(f"{k} {getattr(st, k):.3f}" for k, _ in abi.TraceStats._fields_ if k != "rays"), flush=True)
         lib.rtx_free(ctx, acc)
         lib.rtx_free(ctx, rays)
         lib.rtx_scene_destroy(sc)
