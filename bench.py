@@ -11,6 +11,9 @@ end-of-frame combine; per-GPU work is fixed as N grows ("weak").
   e2e   : the same metric through the public API with HOST buffers: every step uploads the scene
           description (rtx_scene_create: H2D), renders, combines, tonemaps and reads the RGBA8
           frame back to the host (D2H) inside the timed region
+  frames : the jobs BASELINE.json's metric names, timed once each with the same barrier / event bracket — `final_10k`
+          (scene 9, 800x800, 10 000 spp IN TOTAL, split over the N ranks: STRONG scaling, efficiency = T(1) / (N T(N)))
+          and `cornell_box` / `cornell_smoke` (scenes 7 and 8, 600x600, --cornell-spp in total)
   --impl reference : the reference's own CPU implementation of the path (the C++ f64 oracle — the
           Rust reference cannot be built here), all host threads, on a bounded sample of the frame
 """
@@ -30,6 +33,11 @@ if ROOT not in sys.path:
 SCENE = 9
 METRIC = "path samples/sec"
 UNIT = "samples/s"
+# the scene table of src/main.rs:66-183 (width, height, samples per pixel, max depth, name), for the CPU arm, which must
+# not load the product library; the GPU arm checks it against rtx_builtin_scene_defaults
+SCENE_TABLE = {1: (400, 225, 100, 50, "random_scene"), 2: (400, 225, 100, 50, "two_spheres"), 3: (400, 225, 100, 50, "two_perlin_spheres"),
+               4: (400, 225, 100, 50, "earth"), 5: (400, 225, 400, 50, "simple_light"), 6: (600, 600, 200, 50, "empty_cornell_box"),
+               7: (600, 600, 200, 50, "cornell_box"), 8: (600, 600, 200, 50, "smoke_cornell_box"), 9: (800, 800, 10000, 50, "final_scene")}
 
 
 def parse():
@@ -42,62 +50,91 @@ def parse():
     ap.add_argument("--scene", type=int, default=SCENE)
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
-    ap.add_argument("--combine", default="auto", choices=["auto", "peer", "nccl"])
+    ap.add_argument("--combine", default="auto", choices=["auto", "peer", "slice", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
+    ap.add_argument("--no-frames", action="store_true", help="skip the final_10k / Cornell frames")
+    ap.add_argument("--final-spp", type=int, default=10000, help="total spp of the final_10k frame (the reference default)")
+    ap.add_argument("--cornell-spp", type=int, default=8000, help="total spp of the Cornell frames (reference default 200: too short to time)")
     return ap.parse_args()
 
 
+def scene_defaults(number):
+    w, h, spp, depth, name = SCENE_TABLE[number]
+    return {"width": w, "height": h, "samples": spp, "max_depth": depth, "name": name}
+
+
 def workload(args):
-    import rttnw_b200 as R
-    d = R.scene_defaults(args.scene)
+    d = scene_defaults(args.scene)
     w, h = args.width or d["width"], args.height or d["height"]
     return d, w, h
 
 
-def issue_roof(ncu, pairs_per_step, ms_per_step, clocks, info):
-    """Warp instructions issued against the SMs' issue slots (4 per clock and SM): how far the wavefront is from
-    the roof SURVEY.md §8d names first. Instruction counts per launch come from the committed ncu captures of the
-    default configuration (profiles/dram_traffic.json): three --set full captures from the expensive middle of a frame
-    of scene 9, scaled to the whole-render mean by the launch durations of profiles/r1_launches.csv (instructions
-    per microsecond are constant to within 10 % across launches, profiles/r1_first_quarter_instructions.csv).
-    The time and the SM clock are this run's. An estimate, good to about a tenth."""
+def kernels_sha():
+    """Hash of the kernel sources: the committed ncu counters are only used when they belong to the sources that run."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rttnw_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_counters(scene):
+    """profiles/r2_counters_s<scene>.json (tools/r2_profile.sh + tools/r2_counters.py): warp instructions, lanes, DRAM
+    and L2 bytes PER PATH SAMPLE of each wavefront kernel, summed over every launch of one render under ncu. Per-sample
+    counts are a property of the build and the scene, not of the run, so they combine with this run's measured
+    samples/s into live rates. A file that was captured on other kernel sources is refused."""
+    path = os.path.join(ROOT, "profiles", f"r2_counters_s{scene}.json")
     try:
-        import torch
-        w = 0.0
-        for k in ("wf_trace_kernel", "wf_shade_kernel"):
-            w += ncu[k + "_warp_instructions"] * ncu[k + "_duration_us_mean_over_a_render"] / ncu[k + "_duration_us_alone"]
-        mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        sms = torch.cuda.get_device_properties(0).multi_processor_count
-        slots = ms_per_step * 1e-3 * mhz * 1e6 * 4 * sms
-        return {"warp_instructions_per_iteration_mean": w, "iterations_per_step": pairs_per_step, "issue_slots_per_step": slots,
-                "frac": w * pairs_per_step / slots, "lanes_active_trace": ncu["wf_trace_kernel_lanes_active_per_warp_instruction"],
-                "lanes_active_shade": ncu["wf_shade_kernel_lanes_active_per_warp_instruction"],
-                "note": "estimate; valid for the configuration the captures were taken on (scene 9, default pool)"}
-    except Exception as e:  # no capture on file
-        return {"unavailable": str(e)}
+        doc = json.load(open(path))
+    except Exception as e:  # noqa: BLE001
+        return None, f"no counters on file ({e})"
+    if doc.get("kernels_sha") != kernels_sha():
+        return None, f"{os.path.basename(path)} was captured on kernel sources {doc.get('kernels_sha')}, these are {kernels_sha()}: re-run tools/r2_profile.sh"
+    return doc, None
 
 
-def config(args, d, w, h, extra=None):
-    c = {"workload": f"scene {args.scene} ({d['name']}) {w}x{h}, max depth {d['max_depth']}, "
-                     f"{args.spp} spp per GPU per step; reference default is {d['samples']} spp per frame",
-         "scene": args.scene, "width": w, "height": h, "spp_per_gpu_per_step": args.spp,
-         "max_depth": d["max_depth"], "sharding": "samples per pixel across GPUs, one combine per step",
-         "l2": "flushed between timed steps (256 MiB write); the scene working set itself is L2-resident by nature"}
-    if extra:
-        c.update(extra)
-    return c
+def issue_roof(counters, samples_per_s, clocks, sms):
+    """Warp instructions issued per second (instructions per path sample from the ncu counters x this run's measured
+    path samples/s) against the SMs' issue slots at the SM clock sampled during the timed region: the roof SURVEY.md
+    §8d names first for this path. Also the warp-execution efficiency (lanes per warp instruction / 32)."""
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    per_sample = sum(k["warp_instructions_per_sample"] for k in counters["kernels"].values())
+    achieved = per_sample * samples_per_s / 1e9
+    peak = 4.0 * sms * mhz * 1e6 / 1e9
+    out = {"achieved": achieved, "peak": peak, "unit": "G warp instructions/s", "frac": achieved / peak,
+           "warp_instructions_per_sample": per_sample, "sm_mhz": mhz, "sms": sms, "kernels": {}}
+    for name, k in counters["kernels"].items():
+        out["kernels"][name] = {"warp_instructions_per_sample": k["warp_instructions_per_sample"],
+                                "lanes_per_warp_instruction": k["lanes_per_warp_instruction"],
+                                "warp_execution_efficiency": k["lanes_per_warp_instruction"] / 32.0,
+                                "instructions_per_active_sm_cycle_alone": k["instructions_per_active_sm_cycle"]}
+    return out
+
+
+def config(args, d, w, h):
+    """The workload, and nothing else: both arms print the same dict (arm-specific facts go to `details`)."""
+    return {"workload": f"scene {args.scene} ({d['name']}) {w}x{h}, max depth {d['max_depth']}, "
+                        f"{args.spp} spp per GPU per step; reference default is {d['samples']} spp per frame",
+            "scene": args.scene, "width": w, "height": h, "spp_per_gpu_per_step": args.spp,
+            "max_depth": d["max_depth"], "sharding": "samples per pixel across GPUs, one combine per step",
+            "l2": "flushed between timed steps (256 MiB write); the scene working set itself is L2-resident by nature"}
 
 
 # ---------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / the reported baseline, never the product)
 # ---------------------------------------------------------------------------
-def oracle_scene(args):
+def oracle_scene(scene):
     import numpy as np
     from PIL import Image
     from tests import _oracle as O
     earth = np.ascontiguousarray(np.asarray(Image.open(os.path.join(ROOT, "assets", "earth.png")).convert("RGBA"), dtype=np.uint8))
-    return O, O.OracleScene.builtin(args.scene, earth=earth)
+    t0 = time.perf_counter()
+    osc = O.OracleScene.builtin(scene, earth=earth)  # scene construction incl. the reference's own BVH build (Q17)
+    return O, osc, time.perf_counter() - t0
 
 
 def cpu_sample(osc, w, h, max_depth, stride, spp, seed, threads):
@@ -108,28 +145,51 @@ def cpu_sample(osc, w, h, max_depth, stride, spp, seed, threads):
     return rows * w * spp, rays, dt
 
 
-def cpu_baseline(args, d, w, h):
-    """Bounded sample of the same workload on all host cores: every `stride`-th row of the frame."""
-    O, osc = oracle_scene(args)
+def cpu_scene_leg(scene, seconds, width=0, height=0):
+    """The oracle on all host cores on a bounded sample of one scene's default frame: every `stride`-th row at a spp
+    sized for ~`seconds` of work. Returns render-only samples/s (b) and, beside it, the time of what src/main.rs:254-256
+    brackets as well (a): scene construction before the render and the PNG encode of the full frame after it."""
+    import numpy as np
+    d = scene_defaults(scene)
+    w, h = width or d["width"], height or d["height"]
+    O, osc, build_s = oracle_scene(scene)
     threads = O.load().orc_hardware_threads()
-    stride = 16
+    stride = 16 if h >= 400 else 4
     n, rays, dt = cpu_sample(osc, w, h, d["max_depth"], stride, 1, 99, threads)  # calibration (also warms caches)
-    rate = n / max(dt, 1e-6)
-    spp = max(1, int(args.cpu_seconds * rate / n))
+    spp = max(1, int(seconds * (n / max(dt, 1e-6)) / n))
     n, rays, dt = cpu_sample(osc, w, h, d["max_depth"], stride, spp, 100, threads)
-    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    # the PNG of a full frame (zlib level 6 like the `png` crate's default), timed on a gradient of the same size
+    import io
+    from PIL import Image
+    frame = (np.indices((h, w)).sum(axis=0) % 251).astype(np.uint8)
+    t0 = time.perf_counter()
+    Image.fromarray(np.stack([frame] * 3 + [np.full_like(frame, 255)], axis=2), "RGBA").save(io.BytesIO(), format="PNG")
+    png_s = time.perf_counter() - t0
+    rate = n / dt
+    full = w * h * d["samples"]
+    return {"scene": scene, "name": d["name"], "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "rays_per_sample": rays / n,
             "sample": f"every {stride}th row of the {w}x{h} frame ({len(range(stride // 2, h, stride))} rows) x {spp} spp = "
                       f"{n} path samples, {rays} rays, {dt:.2f} s; C++ f64 oracle (the Rust reference cannot be built here)",
-            "rays_per_sample": rays / n}
+            "default_frame": {"path_samples": full, "render_s_extrapolated": full / rate, "scene_build_s": build_s, "png_encode_s": png_s,
+                              "build_render_png_s_extrapolated": build_s + full / rate + png_s,
+                              "note": "BASELINE.md §3: (a) build + render + PNG as src/main.rs:254-256 times it, (b) render only; "
+                                      "the render is linear in spp (src/main.rs:211) and extrapolated from the sample"}}
+
+
+def cpu_baseline(args):
+    """Scene 9 (the headline) with most of the budget, scenes 1, 7 and 8 with a few seconds each."""
+    main = cpu_scene_leg(args.scene, args.cpu_seconds, args.width, args.height)
+    main["other_scenes"] = [cpu_scene_leg(sc, max(1.0, args.cpu_seconds / 5)) for sc in (1, 7, 8) if sc != args.scene]
+    return main
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import rttnw_b200 as R  # host-side scene table only
     d, w, h = workload(args)
-    O, osc = oracle_scene(args)
+    O, osc, _ = oracle_scene(args.scene)
     threads = O.load().orc_hardware_threads()
     stride = 16
     n, rays, dt = cpu_sample(osc, w, h, d["max_depth"], stride, 1, 7, threads)
@@ -148,7 +208,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config(args, d, w, h, {"note": "CPU arm: one host process regardless of --gpus"}),
+            "config": config(args, d, w, h),
+            "details": {"note": "CPU arm: one host process regardless of --gpus"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "rays_per_sec": total_rays / total_t,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -207,8 +268,104 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+class Frame:
+    """One accumulator + RGBA8 frame of a given size on this rank, with the multi-GPU combine wired up:
+      peer  : rank 0's fused reduce + tonemap kernel reads the other accumulators over NVLink (CUDA-IPC mappings)
+      slice : every rank reduces + tonemaps 1/N of the pixels and writes them into rank 0's frame (rtx_reduce_tonemap_slice)
+      nccl  : rtx_accum_reduce (ncclReduce on the ctx stream, behind the C ABI) + rtx_tonemap_rgba8 on rank 0
+    Accumulators are raw cudaMalloc blocks so that they can be exported over CUDA IPC."""
+
+    def __init__(self, env, w, h, combine):
+        import torch
+        self.env, self.w, self.h = env, w, h
+        lib, ctx, abi, dist = env["lib"], env["ctx"], env["abi"], env["dist"]
+        rank, world, dev = env["rank"], env["world"], env["dev"]
+        self.n_px = w * h
+        self.acc_bytes = self.n_px * 16
+        self.accum = C.c_void_p()
+        abi.check(lib.rtx_malloc(ctx.h, self.acc_bytes, C.byref(self.accum)))
+        self.rgba_p = C.c_void_p()
+        abi.check(lib.rtx_malloc(ctx.h, self.n_px * 4, C.byref(self.rgba_p)))
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (self.rgba_p.value, False), "version": 2}
+        self.d_rgba = torch.as_tensor(_Arr(), device=dev)
+        self.rgba_host = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+        self.combine = "local" if world == 1 else combine
+        self.all_acc = self.root_rgba = self.peers = self.comm = None
+        if world == 1:
+            return
+        if self.combine in ("auto", "peer", "slice"):
+            try:
+                def export(ptr):
+                    hd = (C.c_uint8 * 64)()
+                    abi.check(lib.rtx_ipc_export(ctx.h, ptr, C.byref(hd)))
+                    return bytes(hd)
+                handles = [None] * world
+                dist.all_gather_object(handles, (export(self.accum), export(self.rgba_p)))
+
+                def open_(hb):
+                    hd = (C.c_uint8 * 64).from_buffer_copy(hb)
+                    p = C.c_void_p()
+                    abi.check(lib.rtx_ipc_open(ctx.h, C.byref(hd), C.byref(p)))
+                    return p.value
+                ptrs = [self.accum.value if r == rank else open_(handles[r][0]) for r in range(world)]
+                self.all_acc = (C.c_void_p * world)(*ptrs)
+                self.peers = (C.c_void_p * (world - 1))(*[ptrs[r] for r in range(world) if r != 0]) if rank == 0 else None
+                self.root_rgba = self.rgba_p.value if rank == 0 else open_(handles[0][1])
+                ok = torch.ones(1, device=dev)
+            except Exception as e:  # noqa: BLE001
+                if self.combine != "auto":
+                    raise
+                sys.stderr.write(f"[rank {rank}] CUDA IPC unavailable ({e}); combining with NCCL\n")
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() <= 0:
+                self.combine = "nccl"
+            elif self.combine == "auto":
+                self.combine = "peer"
+        if self.combine == "nccl":
+            ident = (C.c_uint8 * 128)()
+            if rank == 0:
+                abi.check(lib.rtx_comm_unique_id(C.byref(ident)))
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=0)
+            ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+            self.comm = C.c_void_p()
+            abi.check(lib.rtx_comm_create(ctx.h, world, rank, C.byref(ident), C.byref(self.comm)))
+
+    def zero(self):
+        self.env["abi"].check(self.env["lib"].rtx_memset_zero(self.env["ctx"].h, self.accum, self.acc_bytes))
+
+    def render(self, scene_h, spp_begin, spp_count, max_depth, ray_counter=None):
+        abi, lib, ctx = self.env["abi"], self.env["lib"], self.env["ctx"]
+        p = abi.RenderParams(self.w, self.h, spp_begin, spp_count, max_depth, 0, 1)
+        rc = C.c_void_p(ray_counter.data_ptr()) if ray_counter is not None else None
+        abi.check(lib.rtx_render(ctx.h, scene_h, C.byref(p), self.accum, rc))
+
+    def combine_and_tonemap(self):
+        """every rank's accumulator -> RGBA8 frame on rank 0 (device)."""
+        abi, lib, ctx, rank, world = self.env["abi"], self.env["lib"], self.env["ctx"], self.env["rank"], self.env["world"]
+        barrier = self.env["barrier"]
+        if self.combine == "peer":
+            barrier()  # every rank's accumulator is complete
+            if rank == 0:
+                abi.check(lib.rtx_reduce_tonemap_peers(ctx.h, self.accum, self.peers, world - 1, self.w, self.h, self.rgba_p))
+            barrier()  # peers may overwrite their accumulators again
+        elif self.combine == "slice":
+            barrier()
+            abi.check(lib.rtx_reduce_tonemap_slice(ctx.h, self.all_acc, world, rank, self.w, self.h, C.c_void_p(self.root_rgba)))
+            barrier()
+        elif self.combine == "nccl":
+            abi.check(lib.rtx_accum_reduce(ctx.h, self.comm, self.accum, self.w, self.h, 0))
+            if rank == 0:
+                abi.check(lib.rtx_tonemap_rgba8(ctx.h, self.accum, self.w, self.h, self.rgba_p, 1))
+        else:
+            abi.check(lib.rtx_reduce_tonemap_peers(ctx.h, self.accum, None, 0, self.w, self.h, self.rgba_p))
+
+
 def run_ours(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
@@ -226,6 +383,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d, w, h = workload(args)
+    assert R.scene_defaults(args.scene) == scene_defaults(args.scene), "bench.py's scene table disagrees with the library's"
     lib = abi.load()
     ctx = R.Context(local)
     desc = R.BuiltinDesc(args.scene)
@@ -233,87 +391,34 @@ def run_ours(args):
     info = scene.info()
     dev = torch.device("cuda", local)
     n_px = w * h
-    acc_bytes = n_px * 16
-
-    # accumulators are raw cudaMalloc blocks so that they can be exported over CUDA IPC
-    def dmalloc(nbytes):
-        p = C.c_void_p()
-        abi.check(lib.rtx_malloc(ctx.h, nbytes, C.byref(p)))
-        return p
-    accum = dmalloc(acc_bytes)
-    d_rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
-    rgba_host = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
-    ray_counter = torch.zeros(1, dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    combine = args.combine
-    peers = None
-    if world > 1 and combine in ("auto", "peer"):
-        try:
-            handle = (C.c_uint8 * 64)()
-            abi.check(lib.rtx_ipc_export(ctx.h, accum, C.byref(handle)))
-            handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle))
-            if rank == 0:
-                ptrs = []
-                for r in range(1, world):
-                    hb = (C.c_uint8 * 64).from_buffer_copy(handles[r])
-                    p = C.c_void_p()
-                    abi.check(lib.rtx_ipc_open(ctx.h, C.byref(hb), C.byref(p)))
-                    ptrs.append(p.value)
-                peers = (C.c_void_p * len(ptrs))(*ptrs)
-            ok = torch.ones(1, device=dev)
-        except Exception as e:  # noqa: BLE001
-            if combine == "peer":
-                raise
-            sys.stderr.write(f"[rank {rank}] CUDA IPC unavailable ({e}); combining with NCCL\n")
-            ok = torch.zeros(1, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        combine = "peer" if ok.item() > 0 else "nccl"
-    elif world > 1:
-        combine = "nccl"
-    else:
-        combine = "local"
-    acc_view = None
-    if combine == "nccl":
-        # a torch view of the raw accumulator for torch.distributed
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (n_px * 4,), "typestr": "<f4", "data": (accum.value, False), "version": 2}
-        acc_view = torch.as_tensor(_Arr(), device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
-
+    env = {"lib": lib, "ctx": ctx, "abi": abi, "dist": dist, "rank": rank, "world": world, "dev": dev, "barrier": barrier}
+    frame = Frame(env, w, h, args.combine)
+    combine = frame.combine
+    ray_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     step_no = [0]
 
     def render_step(sc):
         """render spp samples/pixel on this rank, combine on rank 0, tonemap (device RGBA8)."""
         k = step_no[0]
         step_no[0] += 1
-        abi.check(lib.rtx_memset_zero(ctx.h, accum, acc_bytes))
-        p = abi.RenderParams(w, h, (k * world + rank) * args.spp, args.spp, d["max_depth"], 0, 1)
-        abi.check(lib.rtx_render(ctx.h, sc.h, C.byref(p), accum, C.c_void_p(ray_counter.data_ptr())))
-        if combine == "peer":
-            barrier()  # every rank's accumulator is complete
-            if rank == 0:
-                abi.check(lib.rtx_reduce_tonemap_peers(ctx.h, accum, peers, world - 1, w, h, C.c_void_p(d_rgba.data_ptr())))
-            barrier()  # peers may overwrite their accumulators again
-        elif combine == "nccl":
-            dist.reduce(acc_view, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                abi.check(lib.rtx_tonemap_rgba8(ctx.h, accum, w, h, C.c_void_p(d_rgba.data_ptr()), 1))
-        else:
-            abi.check(lib.rtx_reduce_tonemap_peers(ctx.h, accum, None, 0, w, h, C.c_void_p(d_rgba.data_ptr())))
+        frame.zero()
+        frame.render(sc.h, (k * world + rank) * args.spp, args.spp, d["max_depth"], ray_counter)
+        frame.combine_and_tonemap()
 
-    def timed(fn, steps, sampler=None):
+    def timed(fn, steps, sampler=None, flush_l2=True):
         barrier()
         torch.cuda.synchronize()
         t0 = time.monotonic()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(steps):
-            flush.fill_(1)  # evict L2 between timed steps
+            if flush_l2:
+                flush.fill_(1)  # evict L2 between timed steps
             fn()
         ev1.record()
         torch.cuda.synchronize()
@@ -330,32 +435,20 @@ def run_ours(args):
         flush.fill_(1)
         render_step(scene)
     ray_counter.zero_()
-    # the render kernel alone, for the roofline (events on the launching stream, inside the timed region)
+    # the render call alone, for the roofline (events on the launching stream, inside the timed region)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     it = iter(kev)
-    real_lib = lib
 
     def step_resident():
         e0, e1 = next(it)
         k = step_no[0]
         step_no[0] += 1
-        abi.check(real_lib.rtx_memset_zero(ctx.h, accum, acc_bytes))
-        p = abi.RenderParams(w, h, (k * world + rank) * args.spp, args.spp, d["max_depth"], 0, 1)
+        frame.zero()
         e0.record()
-        abi.check(real_lib.rtx_render(ctx.h, scene.h, C.byref(p), accum, C.c_void_p(ray_counter.data_ptr())))
+        frame.render(scene.h, (k * world + rank) * args.spp, args.spp, d["max_depth"], ray_counter)
         e1.record()
-        if combine == "peer":
-            barrier()
-            if rank == 0:
-                abi.check(real_lib.rtx_reduce_tonemap_peers(ctx.h, accum, peers, world - 1, w, h, C.c_void_p(d_rgba.data_ptr())))
-            barrier()
-        elif combine == "nccl":
-            dist.reduce(acc_view, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                abi.check(real_lib.rtx_tonemap_rgba8(ctx.h, accum, w, h, C.c_void_p(d_rgba.data_ptr()), 1))
-        else:
-            abi.check(real_lib.rtx_reduce_tonemap_peers(ctx.h, accum, None, 0, w, h, C.c_void_p(d_rgba.data_ptr())))
-    ctx.set_profiling(True)  # CUDA events around every shade / trace launch, on the launching stream
+        frame.combine_and_tonemap()
+    ctx.set_profiling(True)  # CUDA events around every 8th shade / trace launch, on the launching stream
     ctx.profile_read(reset=True)
     launches0 = ctx.kernel_launches()
     total_ms, clocks = timed(step_resident, args.steps, sampler)
@@ -373,7 +466,6 @@ def run_ours(args):
 
     # ---- end to end through the public API, host buffers ----
     h2d = [0]
-
     e2e_log = []
 
     def step_e2e():
@@ -385,7 +477,7 @@ def run_ours(args):
         render_step(sc)
         t2 = time.perf_counter()
         if rank == 0:
-            rgba_host.copy_(d_rgba, non_blocking=True)  # D2H of the frame
+            frame.rgba_host.copy_(frame.d_rgba, non_blocking=True)  # D2H of the frame
         torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
         sc.close()
@@ -399,6 +491,44 @@ def run_ours(args):
     if rank == 0:
         sys.stderr.write("e2e host phases per step (scene create, render call, sync + D2H, scene destroy) ms: " +
                          "; ".join("/".join(f"{1e3 * x:.1f}" for x in row) for row in e2e_log) + "\n")
+
+    # ---- the frames BASELINE.json's metric names: final scene at 10 000 spp in total (strong scaling), Cornell boxes ----
+    frames = {}
+    if not args.no_frames:
+        def one_frame(number, spp_total, fr, sc):
+            dd = scene_defaults(number)
+            begin, count = R.shard_spp(spp_total, rank, world)
+            rc = torch.zeros(1, dtype=torch.int64, device=dev)
+
+            def go():
+                fr.zero()
+                chunk = 1 << 12  # (rtx_render takes up to 2^26 spp per call; chunks keep the sample index arithmetic in range)
+                for b0 in range(begin, begin + count, chunk):
+                    fr.render(sc.h, b0, min(chunk, begin + count - b0), dd["max_depth"], rc)
+                fr.combine_and_tonemap()
+                if rank == 0:
+                    fr.rgba_host.copy_(fr.d_rgba, non_blocking=True)
+            ms, _ = timed(go, 1, flush_l2=False)
+            rt = torch.tensor([float(rc.item())], device=dev)
+            if world > 1:
+                dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+            n = fr.w * fr.h * spp_total
+            return {"scene": number, "name": dd["name"], "width": fr.w, "height": fr.h, "spp_total": spp_total, "spp_per_gpu": count,
+                    "seconds": ms * 1e-3, "value": n / (ms * 1e-3), "unit": UNIT, "rays_per_sec": rt.item() / (ms * 1e-3),
+                    "scaling": "strong", "timed": "zero + render (this rank's share of the spp) + combine + tonemap + D2H of the frame, "
+                    "barrier + synchronize on both sides, max over ranks; run once after the warm-up of the step loop",
+                    "reference_default_spp": dd["samples"]}
+        if args.scene == 9 and (w, h) == (800, 800):
+            frames["final_10k"] = one_frame(9, args.final_spp, frame, scene)
+        for name, number in (("cornell_box", 7), ("cornell_smoke", 8)):
+            dd = scene_defaults(number)
+            sc = R.DeviceScene(ctx, R.BuiltinDesc(number))
+            fr = Frame(env, dd["width"], dd["height"], combine if combine != "local" else args.combine)
+            fr.zero()
+            fr.render(sc.h, 0, 8, dd["max_depth"])  # warm-up (pool allocation for this size)
+            ctx.sync()
+            frames[name] = one_frame(number, args.cornell_spp, fr, sc)
+            sc.close()
 
     # ---- roofline bookkeeping (rank 0, outside the timed region): counting build of the kernel ----
     line = None
@@ -416,50 +546,69 @@ def run_ours(args):
         trace_launches = max(1, launches // 2) if prof["iterations"] else args.steps
         kms = prof["trace_ms"] / n_it if prof["iterations"] else sum(kern_ms) / len(kern_ms)  # (megakernel mode: one launch per step)
         rays_per_launch = rays_rank / trace_launches
-        achieved = a_ray * rays_per_launch / (kms * 1e-3) / 1e9
+        algo_gbs = a_ray * rays_per_launch / (kms * 1e-3) / 1e9
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
-        ncu = {}
-        try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-            traffic = ncu.get("wf_trace_kernel_dram_bytes_per_launch")
-        except Exception:
-            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        counters, why_not = load_counters(args.scene)
+        samples_per_s_rank = value / world
         # the roof that does bound the node traffic: L2 read bandwidth, measured on this GPU now (l2_gbs)
         l2_gbs = ctx.measure_l2_read()
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "wf_trace_kernel" if prof["iterations"] else "render_kernel", "kernel_ms_per_launch": kms, "launches_per_step": trace_launches / args.steps,
-                    "aggregate_GBps_over_the_step": a_ray * rays_rank / (total_ms * 1e-3) / 1e9,
-                    "kernel_share_of_step": (prof["trace_ms"] if prof["iterations"] else sum(kern_ms)) / total_ms, "shade_kernel_share_of_step": prof["shade_ms"] / total_ms,
-                    "render_call_ms_per_step": sum(kern_ms) / len(kern_ms),
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                    "algorithmic_bytes_per_ray": a_ray, "algorithmic_flops_per_ray": f_ray, "rays_per_launch": rays_per_launch,
-                    "l2": {"peak": l2_gbs, "unit": "GB/s", "frac": achieved / l2_gbs,
-                           "peak_source": "rtx_ctx_measure_l2_read: 16-byte ld.global.cg over a 32 MiB L2-resident buffer, all SMs, this run"},
-                    "ncu": {k: v for k, v in ncu.items() if k.startswith("wf_trace_kernel_") or k == "source"},
-                    "issue": issue_roof(ncu, trace_launches / args.steps, total_ms / args.steps, clocks, info),
-                    "per_ray_means": {k: st[k] for k in ("box_tests", "node_visits", "sphere_tests", "rect_tests", "instance_enters", "medium_tests")},
-                    "note": "the flattened scene (%.1f MB) and the path pool are L2-resident: the algorithmic bytes are the BVH-node and "
-                            "primitive bytes the traversal must fetch, served by L1/L2, so HBM is not what bounds this kernel "
-                            "(latency / issue slots are: see profiles/)" % (info["device_bytes"] / 1e6)}
+        hbm = {"algorithmic": {"achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
+                               "what": "SURVEY.md §8d algorithmic node + primitive bytes per ray x rays per trace launch / the launch's duration: "
+                                       "bytes the traversal must FETCH (from L1/L2: the scene is cache resident), not DRAM traffic"},
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+        traffic = None
+        if counters:
+            dram_per_sample = sum(k["dram_bytes_per_sample"] for k in counters["kernels"].values())
+            l2_per_sample = sum(k["l2_bytes_per_sample"] for k in counters["kernels"].values())
+            tk = counters["kernels"].get("wf_trace_kernel") or {}
+            traffic = tk.get("dram_bytes_per_launch")
+            hbm["dram"] = {"achieved": dram_per_sample * samples_per_s_rank / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": dram_per_sample * samples_per_s_rank / 1e9 / hbm_peak, "bytes_per_sample": dram_per_sample,
+                           "what": "dram__bytes_read + dram__bytes_write of every wavefront launch (ncu, per path sample) x this run's samples/s: "
+                                   "the ray pool and the accumulator; ncu runs each launch alone and cold, so this is an upper bound"}
+            l2 = {"achieved": l2_per_sample * samples_per_s_rank / 1e9, "peak": l2_gbs, "unit": "GB/s",
+                  "frac": l2_per_sample * samples_per_s_rank / 1e9 / l2_gbs, "bytes_per_sample": l2_per_sample,
+                  "algorithmic_frac": algo_gbs / l2_gbs,
+                  "peak_source": "rtx_ctx_measure_l2_read: 16-byte ld.global.cg over a 32 MiB L2-resident buffer, all SMs, this run"}
+            issue = issue_roof(counters, samples_per_s_rank, clocks, sms)
+            roofline = {"bound": "issue", "achieved": issue["achieved"], "peak": issue["peak"], "unit": issue["unit"], "frac": issue["frac"],
+                        "traffic": traffic, "issue": issue, "l2": l2, "hbm": hbm,
+                        "counters": {"file": f"profiles/r2_counters_s{args.scene}.json", "kernels_sha": counters["kernels_sha"], "source": counters["source"]}}
+        else:
+            roofline = {"bound": "issue", "achieved": None, "peak": 4.0 * sms * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                        "unit": "G warp instructions/s", "frac": None, "traffic": None, "hbm": hbm,
+                        "l2": {"peak": l2_gbs, "unit": "GB/s", "algorithmic_frac": algo_gbs / l2_gbs}, "counters": {"unavailable": why_not}}
+        roofline.update({
+            "kernel": "wf_trace_kernel" if prof["iterations"] else "render_kernel", "kernel_ms_per_launch": kms,
+            "launches_per_step": trace_launches / args.steps,
+            "kernel_share_of_step": (prof["trace_ms"] if prof["iterations"] else sum(kern_ms)) / total_ms,
+            "shade_kernel_share_of_step": prof["shade_ms"] / total_ms, "render_call_ms_per_step": sum(kern_ms) / len(kern_ms),
+            "algorithmic_bytes_per_ray": a_ray, "algorithmic_flops_per_ray": f_ray, "rays_per_launch": rays_per_launch,
+            "per_ray_means": {k: st[k] for k in ("box_tests", "node_visits", "sphere_tests", "rect_tests", "instance_enters", "medium_tests")},
+            "note": "the flattened scene (%.1f MB) and the path pool are L2-resident: what bounds the wavefront is issue slots at the lane "
+                    "utilisation divergence leaves (warp_execution_efficiency) and the latency the resident warps cannot cover; HBM and "
+                    "L2 bandwidth are far from their roofs (hbm.dram.frac, l2.frac)" % (info["device_bytes"] / 1e6)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "dtype_note": "f64 rays, primitive tests, hit points and scatter directions; fp32 BVH boxes (conservative), "
                 "textures, throughput and accumulation", "data": "synthetic",
-                "config": config(args, d, w, h, {"combine": combine, "bvh_nodes": info["bvh_nodes"], "records": info["records"],
-                                                 "scene_bytes": info["device_bytes"]}),
+                "config": config(args, d, w, h),
+                "details": {"combine": combine, "bvh_nodes": info["bvh_nodes"], "records": info["records"], "scene_bytes": info["device_bytes"],
+                            "kernels_sha": kernels_sha()},
                 "rays_per_sec": rays_total / (total_ms * 1e-3), "rays_per_sample": rays_total / samples_total,
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": n_px * 4,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "frames": frames,
                 "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, d, w, h)
+            line["cpu_baseline"] = cpu_baseline(args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -290,9 +290,32 @@ int rtx_tonemap_rgba8(rtx_ctx* ctx, const float* d_accum, int32_t width, int32_t
                       uint8_t* out, int out_on_device);
 /* Rank-0 side of the multi-GPU combine: sums n_peers device accumulators
  * (peer-mapped pointers, read over NVLink) into d_accum and tonemaps in the
- * same kernel. d_rgba8 is a device buffer. Asynchronous. */
+ * same kernel. d_rgba8 is a device buffer. Asynchronous. DESTRUCTIVE: d_accum
+ * receives the sum (so that rank 0 can checkpoint or keep accumulating the
+ * combined frame) — call it once per frame, a second call would add the peers
+ * again. A peer on a device this one cannot map (no NVLink / PCIe peer-to-peer)
+ * is staged through a scratch buffer with cudaMemcpyPeerAsync instead. */
 int rtx_reduce_tonemap_peers(rtx_ctx* ctx, float* d_accum, const float* const* d_peer_accums,
                              int32_t n_peers, int32_t width, int32_t height, uint8_t* d_rgba8);
+
+/* The same combine with the work spread over the ranks: EVERY rank calls this with the accumulators of all n_ranks
+ * ranks (its own and the peer-mapped / IPC-opened others, in rank order) and reduces + tonemaps pixels
+ * [rank * n / n_ranks, (rank + 1) * n / n_ranks) only, writing them straight into rank 0's RGBA8 buffer
+ * (d_rgba8_root: local on rank 0, peer-mapped elsewhere). Nothing is written back to the accumulators, so unlike
+ * rtx_reduce_tonemap_peers it can be repeated. The caller orders the ranks (a barrier before and after). */
+int rtx_reduce_tonemap_slice(rtx_ctx* ctx, const float* const* d_accums, int32_t n_ranks, int32_t rank,
+                             int32_t width, int32_t height, uint8_t* d_rgba8_root);
+/* NCCL form of the combine (the fold of src/main.rs:211-217 across ranks as one
+ * ncclReduce(sum, float, width*height*4) to `root`, in place, on the ctx stream; follow it with rtx_tonemap_rgba8 on
+ * the root). libnccl.so.2 is opened at the first call — RTX_ERR_UNSUPPORTED when the host has none. One rank makes
+ * the 128-byte id and hands it to the others by whatever channel the host has (a pipe, MPI, torch.distributed);
+ * rtx_comm_create is collective over the n_ranks contexts. rtx_comm_wrap adopts an ncclComm_t the host already owns. */
+typedef struct rtx_comm rtx_comm;
+int rtx_comm_unique_id(uint8_t id_out[128]);
+int rtx_comm_create(rtx_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t id[128], rtx_comm** out);
+int rtx_comm_wrap(void* nccl_comm, rtx_comm** out);
+int rtx_comm_destroy(rtx_comm* comm);
+int rtx_accum_reduce(rtx_ctx* ctx, rtx_comm* comm, float* d_accum, int32_t width, int32_t height, int32_t root);
 
 /* ---- device memory + CUDA IPC helpers so that a non-torch host (the Rust
  * crate, the C++ CLI) can drive everything through this ABI alone ---- */

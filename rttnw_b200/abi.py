@@ -126,6 +126,12 @@ SIGNATURES = {
     "rtx_render_counted": (C.c_int, [_P, _P, C.POINTER(RenderParams), _P, C.POINTER(TraceStats)]),
     "rtx_tonemap_rgba8": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int]),
     "rtx_reduce_tonemap_peers": (C.c_int, [_P, _P, C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, _P]),
+    "rtx_reduce_tonemap_slice": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "rtx_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8 * 128)]),
+    "rtx_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_uint8 * 128), C.POINTER(_P)]),
+    "rtx_comm_wrap": (C.c_int, [_P, C.POINTER(_P)]),
+    "rtx_comm_destroy": (C.c_int, [_P]),
+    "rtx_accum_reduce": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32]),
     "rtx_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "rtx_free": (C.c_int, [_P, _P]),
     "rtx_memset_zero": (C.c_int, [_P, _P, C.c_size_t]),

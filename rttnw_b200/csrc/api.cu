@@ -1,6 +1,7 @@
 // api.cu — the C ABI of include/rttnw_b200.h: contexts, scene upload, kernel launches.
 // No entry point computes on the CPU; without a CUDA device they fail with RTX_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -969,31 +970,175 @@ int rtx_tonemap_rgba8(rtx_ctx* c, const float* d_accum, int32_t width, int32_t h
     return RTX_OK;
 }
 
+// Makes `p` (a device pointer, possibly on another device of this process) loadable from ctx's device: enables peer
+// access, or — when the two devices cannot map each other — stages a copy in `scratch` (cudaMemcpyPeerAsync).
+static int map_or_stage_peer(rtx_ctx* c, const float* p, size_t bytes, std::vector<void*>& scratch, const float** out) {
+    *out = p;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device == c->device) {
+        cudaGetLastError();  // IPC-opened pointers are already mapped by rtx_ipc_open; local ones need nothing
+        return RTX_OK;
+    }
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, c->device, at.device);
+    if (can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RTX_OK; }
+    }
+    cudaGetLastError();
+    void* tmp = nullptr;
+    CU(cudaMalloc(&tmp, bytes));
+    scratch.push_back(tmp);
+    CU(cudaMemcpyPeerAsync(tmp, c->device, p, at.device, bytes, c->stream));
+    *out = (const float*)tmp;
+    return RTX_OK;
+}
+
 int rtx_reduce_tonemap_peers(rtx_ctx* c, float* d_accum, const float* const* d_peer_accums, int32_t n_peers, int32_t width,
                              int32_t height, uint8_t* d_rgba8) {
     if (!c || !d_accum || !d_rgba8 || width <= 0 || height <= 0 || n_peers < 0 || (n_peers > 0 && !d_peer_accums))
         return fail(RTX_ERR_INVALID, "bad argument");
     if (n_peers > rtx::kMaxPeers) return fail(RTX_ERR_UNSUPPORTED, "too many peers");
     CU(cudaSetDevice(c->device));
+    const int n = width * height;
     rtx::PeerList pl;
     pl.n = n_peers;
+    std::vector<void*> scratch;
     for (int i = 0; i < n_peers; ++i) {
-        pl.p[i] = reinterpret_cast<const float4*>(d_peer_accums[i]);
-        // same-process peers: make the other GPU's memory loadable from this one (IPC-opened
-        // pointers are already mapped by rtx_ipc_open)
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, d_peer_accums[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
-            at.device != c->device) {
+        const float* q = nullptr;
+        int rc = map_or_stage_peer(c, d_peer_accums[i], (size_t)n * 16, scratch, &q);
+        if (rc != RTX_OK) { for (void* t : scratch) cudaFree(t); return rc; }
+        pl.p[i] = reinterpret_cast<const float4*>(q);
+    }
+    rtx::reduce_tonemap_peers_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<float4*>(d_accum), pl, n,
+                                                                            reinterpret_cast<uchar4*>(d_rgba8));
+    cudaError_t e = cudaGetLastError();
+    if (!scratch.empty()) {  // (the staged path is the slow path: finish before the copies go away)
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        for (void* t : scratch) cudaFree(t);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "reduce_tonemap_peers_kernel");
+    c->launches += 1;
+    return RTX_OK;
+}
+
+int rtx_reduce_tonemap_slice(rtx_ctx* c, const float* const* d_accums, int32_t n_ranks, int32_t rank, int32_t width, int32_t height,
+                             uint8_t* d_rgba8_root) {
+    if (!c || !d_accums || !d_rgba8_root || width <= 0 || height <= 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(RTX_ERR_INVALID, "bad argument");
+    if (n_ranks > rtx::kMaxPeers) return fail(RTX_ERR_UNSUPPORTED, "too many ranks");
+    CU(cudaSetDevice(c->device));
+    const long long n = (long long)width * height;
+    const int first = (int)(n * rank / n_ranks), count = (int)(n * (rank + 1) / n_ranks) - first;
+    rtx::PeerList pl;
+    pl.n = n_ranks;
+    for (int i = 0; i < n_ranks; ++i) {
+        if (!d_accums[i]) return fail(RTX_ERR_INVALID, "NULL accumulator");
+        pl.p[i] = reinterpret_cast<const float4*>(d_accums[i]);
+        cudaPointerAttributes at;  // same-process peers: map the other device (IPC-opened pointers already are)
+        if (cudaPointerGetAttributes(&at, d_accums[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != c->device) {
             cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
         }
         cudaGetLastError();
     }
-    int n = width * height;
-    rtx::reduce_tonemap_peers_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<float4*>(d_accum), pl, n,
-                                                                            reinterpret_cast<uchar4*>(d_rgba8));
-    CU(cudaGetLastError());
-    c->launches += 1;
+    if (count > 0) {
+        rtx::reduce_tonemap_slice_kernel<<<(count + 255) / 256, 256, 0, c->stream>>>(pl, first, count, reinterpret_cast<uchar4*>(d_rgba8_root));
+        CU(cudaGetLastError());
+        c->launches += 1;
+    }
+    return RTX_OK;
+}
+
+// ---- NCCL combine (libnccl.so.2 opened on demand: the library itself does not link against it) ----
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (int (*)(NcclId*))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+        api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclReduce");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Reduce && api.GetErrorString;
+    });
+    return api;
+}
+int nccl_fail(int res, const char* what) {
+    g_err = std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(res) : "NCCL error");
+    return RTX_ERR_CUDA;
+}
+}  // namespace
+
+struct rtx_comm {
+    void* comm = nullptr;  // ncclComm_t
+    bool owned = false;
+};
+
+int rtx_comm_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return fail(RTX_ERR_INVALID, "id_out is NULL");
+    if (!nccl().ok) return fail(RTX_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+    NcclId id;
+    int r = nccl().GetUniqueId(&id);
+    if (r != 0) return nccl_fail(r, "ncclGetUniqueId");
+    std::memcpy(id_out, &id, 128);
+    return RTX_OK;
+}
+int rtx_comm_create(rtx_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t id[128], rtx_comm** out) {
+    if (!c || !id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(RTX_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (!nccl().ok) return fail(RTX_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+    CU(cudaSetDevice(c->device));
+    NcclId nid;
+    std::memcpy(&nid, id, 128);
+    void* comm = nullptr;
+    int r = nccl().CommInitRank(&comm, n_ranks, nid, rank);
+    if (r != 0) return nccl_fail(r, "ncclCommInitRank");
+    rtx_comm* k = new (std::nothrow) rtx_comm();
+    if (!k) { nccl().CommDestroy(comm); return fail(RTX_ERR_NOMEM, "out of host memory"); }
+    k->comm = comm;
+    k->owned = true;
+    *out = k;
+    return RTX_OK;
+}
+int rtx_comm_wrap(void* nccl_comm, rtx_comm** out) {
+    if (!nccl_comm || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    if (!nccl().ok) return fail(RTX_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+    rtx_comm* k = new (std::nothrow) rtx_comm();
+    if (!k) return fail(RTX_ERR_NOMEM, "out of host memory");
+    k->comm = nccl_comm;
+    k->owned = false;
+    *out = k;
+    return RTX_OK;
+}
+int rtx_comm_destroy(rtx_comm* k) {
+    if (!k) return RTX_OK;
+    if (k->owned && k->comm && nccl().ok) nccl().CommDestroy(k->comm);
+    delete k;
+    return RTX_OK;
+}
+int rtx_accum_reduce(rtx_ctx* c, rtx_comm* k, float* d_accum, int32_t width, int32_t height, int32_t root) {
+    if (!c || !k || !k->comm || !d_accum || width <= 0 || height <= 0 || root < 0) return fail(RTX_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    const size_t count = (size_t)width * (size_t)height * 4;
+    int r = nccl().Reduce(d_accum, d_accum, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, root, k->comm, c->stream);
+    if (r != 0) return nccl_fail(r, "ncclReduce");
     return RTX_OK;
 }
 

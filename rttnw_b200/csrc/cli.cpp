@@ -8,8 +8,14 @@
 // next sample index it would render to PATH.<gpu>; --resume reloads them (same scene, size, spp, seed, gpus)
 // and carries on. Samples are keyed by their global index, so a resumed image equals an uninterrupted one up
 // to fp32 summation order.
-// With --gpus N one host thread drives each device; samples are sharded by global sample index
-// and rank 0 sums the peers' accumulators over peer-mapped memory in the tonemap kernel.
+// With --gpus N the samples are sharded by global sample index, one PROCESS per device: the parent forks ranks 1..N-1
+// before it touches CUDA and renders rank 0's share itself, so the N CUDA contexts come up side by side (in one
+// process the driver creates them one after the other: 7.5 s of a 9 s run for eight devices, round 1). Each child
+// hands the parent the CUDA-IPC handle of its accumulator through a pipe and waits; the parent's fused reduce + tonemap
+// kernel reads them over NVLink. RTTNW_SINGLE_PROCESS=1 keeps everything in one process, one thread per device.
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -178,6 +184,97 @@ int main(int argc, char** argv) {
         chk(rtx_ctx_sync(k.ctx));
         if (r == 0) lap("render finished");
     };
+    const bool multi_process = gpus > 1 && std::getenv("RTTNW_SINGLE_PROCESS") == nullptr;
+    struct Child {
+        pid_t pid = -1;
+        int up = -1, down = -1;  // child -> parent: status + IPC handle; parent -> child: release
+    };
+    struct UpMsg {
+        int32_t rc;
+        uint8_t handle[64];
+    };
+    std::vector<Child> children;
+    std::vector<const float*> peers;
+    if (multi_process) {
+        std::fflush(stdout);
+        std::fflush(stderr);
+        for (int r = 1; r < gpus; ++r) {
+            int up[2], down[2];
+            if (pipe(up) != 0 || pipe(down) != 0) { std::perror("pipe"); return 1; }
+            pid_t pid = fork();
+            if (pid < 0) { std::perror("fork"); return 1; }
+            if (pid == 0) {  // rank r: render, publish the accumulator, wait until the parent has read it
+                close(up[0]);
+                close(down[1]);
+                worker(r);
+                Rank& k = ranks[(size_t)r];
+                UpMsg msg;
+                std::memset(&msg, 0, sizeof(msg));
+                msg.rc = k.rc;
+                if (k.rc == 0 && rtx_ipc_export(k.ctx, k.accum, msg.handle) != RTX_OK) {
+                    std::fprintf(stderr, "gpu %d: %s\n", r, rtx_last_error());
+                    msg.rc = 1;
+                }
+                ssize_t w = write(up[1], &msg, sizeof(msg));
+                char go = 0;
+                if (w == (ssize_t)sizeof(msg) && msg.rc == 0) { ssize_t g = read(down[0], &go, 1); (void)g; }
+                if (k.accum) rtx_free(k.ctx, k.accum);
+                if (k.scene) rtx_scene_destroy(k.scene);
+                if (k.ctx) rtx_ctx_destroy(k.ctx);
+                _exit(msg.rc);
+            }
+            close(up[1]);
+            close(down[0]);
+            Child c;
+            c.pid = pid; c.up = up[0]; c.down = down[1];
+            children.push_back(c);
+        }
+        worker(0);
+        int bad = ranks[0].rc;
+        std::vector<void*> opened;
+        for (size_t i = 0; i < children.size(); ++i) {
+            UpMsg msg;
+            ssize_t got = read(children[i].up, &msg, sizeof(msg));
+            if (got != (ssize_t)sizeof(msg)) { msg.rc = 1; std::fprintf(stderr, "gpu %zu: worker process died\n", i + 1); }
+            if (msg.rc != 0 && bad == 0) bad = msg.rc;
+            if (msg.rc == 0 && bad == 0) {
+                void* p = nullptr;
+                if (rtx_ipc_open(ranks[0].ctx, msg.handle, &p) != RTX_OK) { std::fprintf(stderr, "rtx_ipc_open: %s\n", rtx_last_error()); bad = 1; }
+                else { opened.push_back(p); peers.push_back((const float*)p); }
+            }
+        }
+        auto release_children = [&]() {
+            for (auto& c : children) {
+                char go = 1;
+                ssize_t w = write(c.down, &go, 1);
+                (void)w;
+                close(c.down);
+                close(c.up);
+                int status = 0;
+                waitpid(c.pid, &status, 0);
+            }
+        };
+        if (bad != 0) { release_children(); return bad == 3 ? 3 : 1; }
+        lap("all ranks finished");
+        std::vector<uint8_t> rgba_mp((size_t)width * height * 4);
+        uint8_t* d_rgba_mp = nullptr;
+        RTX(rtx_malloc(ranks[0].ctx, rgba_mp.size(), (void**)&d_rgba_mp));
+        RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.empty() ? nullptr : peers.data(), (int)peers.size(), width, height, d_rgba_mp));
+        RTX(rtx_memcpy_d2h(ranks[0].ctx, rgba_mp.data(), d_rgba_mp, rgba_mp.size()));
+        lap("frame on the host");
+        for (void* p : opened) rtx_ipc_close(ranks[0].ctx, p);
+        release_children();
+        RTX(rtx_png_write_rgba8(out.c_str(), width, height, rgba_mp.data()));
+        lap("png written");
+        rtx_free(ranks[0].ctx, d_rgba_mp);
+        rtx_free(ranks[0].ctx, ranks[0].accum);
+        rtx_scene_destroy(ranks[0].scene);
+        rtx_ctx_destroy(ranks[0].ctx);
+        rtx_scene_desc_free(desc);
+        double secs_mp = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("%.6fs\n", secs_mp);  // println!("{:?}", instant.elapsed())
+        return 0;
+    }
     std::vector<std::thread> th;
     for (int r = 0; r < gpus; ++r) th.emplace_back(worker, r);
     for (auto& t : th) t.join();
@@ -187,7 +284,6 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> rgba((size_t)width * height * 4);
     uint8_t* d_rgba = nullptr;
     RTX(rtx_malloc(ranks[0].ctx, rgba.size(), (void**)&d_rgba));
-    std::vector<const float*> peers;
     for (int r = 1; r < gpus; ++r) peers.push_back(ranks[(size_t)r].accum);
     RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.empty() ? nullptr : peers.data(), (int)peers.size(), width, height, d_rgba));
     RTX(rtx_memcpy_d2h(ranks[0].ctx, rgba.data(), d_rgba, rgba.size()));

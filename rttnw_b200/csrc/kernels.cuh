@@ -1384,6 +1384,21 @@ __global__ void reduce_tonemap_peers_kernel(float4* __restrict__ accum, PeerList
     out[i] = make_uchar4(quantise(a.x, inv), quantise(a.y, inv), quantise(a.z, inv), 255);
 }
 
+// The same combine spread over the ranks: this rank's slice of the pixels, every rank's accumulator read (its own
+// locally, the others over NVLink), the RGBA8 result written straight into rank 0's frame. Nothing written back.
+__global__ void reduce_tonemap_slice_kernel(PeerList all, int first, int count, uchar4* __restrict__ out_root) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    i += first;
+    float4 a = all.p[0][i];
+    for (int k = 1; k < all.n; ++k) {
+        float4 b = all.p[k][i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float inv = 1.0f / a.w;
+    out_root[i] = make_uchar4(quantise(a.x, inv), quantise(a.y, inv), quantise(a.z, inv), 255);
+}
+
 // ---------------------------------------------------------------------------
 // Measurement aid (rtx_ctx_measure_l2_read): every thread streams 16-byte words of a buffer that fits in L2,
 // `repeats` times over, with loads that bypass L1 (ld.global.cg). Four independent loads in flight per thread.

@@ -163,6 +163,7 @@ pub struct rtx_scene_defaults {
 
 pub enum rtx_ctx {}
 pub enum rtx_scene {}
+pub enum rtx_comm {}
 
 extern "C" {
     pub fn rtx_abi_version() -> c_int;
@@ -187,6 +188,12 @@ extern "C" {
     pub fn rtx_render_counted(ctx: *mut rtx_ctx, scene: *const rtx_scene, params: *const rtx_render_params, d_accum: *mut f32, out: *mut rtx_trace_stats) -> c_int;
     pub fn rtx_tonemap_rgba8(ctx: *mut rtx_ctx, d_accum: *const f32, width: i32, height: i32, out: *mut u8, out_on_device: c_int) -> c_int;
     pub fn rtx_reduce_tonemap_peers(ctx: *mut rtx_ctx, d_accum: *mut f32, d_peer_accums: *const *const f32, n_peers: i32, width: i32, height: i32, d_rgba8: *mut u8) -> c_int;
+    pub fn rtx_reduce_tonemap_slice(ctx: *mut rtx_ctx, d_accums: *const *const f32, n_ranks: i32, rank: i32, width: i32, height: i32, d_rgba8_root: *mut u8) -> c_int;
+    pub fn rtx_comm_unique_id(id_out: *mut u8) -> c_int;
+    pub fn rtx_comm_create(ctx: *mut rtx_ctx, n_ranks: i32, rank: i32, id: *const u8, out: *mut *mut rtx_comm) -> c_int;
+    pub fn rtx_comm_wrap(nccl_comm: *mut c_void, out: *mut *mut rtx_comm) -> c_int;
+    pub fn rtx_comm_destroy(comm: *mut rtx_comm) -> c_int;
+    pub fn rtx_accum_reduce(ctx: *mut rtx_ctx, comm: *mut rtx_comm, d_accum: *mut f32, width: i32, height: i32, root: i32) -> c_int;
     pub fn rtx_malloc(ctx: *mut rtx_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn rtx_free(ctx: *mut rtx_ctx, ptr: *mut c_void) -> c_int;
     pub fn rtx_memset_zero(ctx: *mut rtx_ctx, ptr: *mut c_void, bytes: usize) -> c_int;

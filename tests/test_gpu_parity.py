@@ -629,3 +629,98 @@ def test_wide_bvh_traversal_finds_the_same_hits(number, monkeypatch):
     finally:
         plain.close()
         wide.close()
+
+
+# ---------------------------------------------------------------------------
+# round 2: the other kernel forms, the spread-out combine, NCCL behind the ABI, one process per GPU
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("form", ["RTX_TRACE=2", "RTX_TRACE=2 RTX_T_REFILL=16 RTX_T_LEAF=8 RTX_T_BURST=8", "RTX_TRACE=3 RTX_T_BURST=4",
+                                  "RTX_TRACE=4", "RTX_SHADE=1"])
+@pytest.mark.parametrize("number", [7, 9])
+def test_other_kernel_forms_trace_the_same_rays(form, number, monkeypatch, earth_rgba):
+    """Every opt-in form of the trace kernel (shared-memory BVH + persistent voted warps, sorted through shared memory,
+    shared stack + 32-byte loads) and the first form of the shade kernel: the same rays, the same samples in the same
+    pixels as the default pair (closest hits do not depend on the traversal order; fp32 atomics reorder the sums) —
+    and the default pair is what every other test compares with the oracle."""
+    base = R.Context(0)
+    for kv in form.split():
+        k, v = kv.split("=")
+        monkeypatch.setenv(k, v)
+    other = R.Context(0)
+    try:
+        out = []
+        for c in (base, other):
+            gsc = R.DeviceScene(c, R.BuiltinDesc(number))
+            acc = gsc.new_accum(160, 120)
+            st = gsc.render_counted(acc, 0, 24, seed=11, max_depth=50)
+            out.append((acc.cpu().numpy(), st))
+            gsc.close()
+        (a, sa), (b, sb) = out
+        assert sa["rays"] == sb["rays"] and sa["rays"] > 0
+        assert (a[..., 3] == 24).all() and (b[..., 3] == 24).all()
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-4)
+    finally:
+        base.close()
+        other.close()
+
+
+def test_reduce_tonemap_slice_single_device(ctx):
+    """rtx_reduce_tonemap_slice with every 'rank' on one device: the slices tile the frame, nothing is written back."""
+    import ctypes as C
+    import torch
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(7))
+    accs = []
+    for r in range(3):
+        b, c = R.shard_spp(48, r, 3)
+        a = gsc.new_accum(33, 31)  # 1023 pixels: the slices are ragged
+        gsc.render_into(a, b, c, seed=9)
+        accs.append(a)
+    keep = [a.clone() for a in accs]
+    expect = gsc.tonemap(accs[0] + accs[1] + accs[2])
+    out = torch.zeros((31, 33, 4), dtype=torch.uint8, device="cuda")
+    ptrs = (C.c_void_p * 3)(*[a.data_ptr() for a in accs])
+    for r in range(3):
+        abi.check(ctx.lib.rtx_reduce_tonemap_slice(ctx.h, ptrs, 3, r, 33, 31, out.data_ptr()))
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), expect)
+    assert all(torch.equal(a, k) for a, k in zip(accs, keep))
+    assert ctx.lib.rtx_reduce_tonemap_slice(ctx.h, ptrs, 3, 3, 33, 31, out.data_ptr()) == -1  # rank out of range
+
+
+def test_nccl_reduce_behind_the_abi_one_rank(ctx):
+    """rtx_comm_* / rtx_accum_reduce with a communicator of one rank (the N-rank path runs in bench.py --combine nccl):
+    libnccl is found, the reduce runs on the ctx stream and leaves the sum (= the accumulator) in place."""
+    import ctypes as C
+    lib = ctx.lib
+    ident = (C.c_uint8 * 128)()
+    rc = lib.rtx_comm_unique_id(C.byref(ident))
+    if rc == -5:
+        pytest.skip("no libnccl.so.2 on this host")
+    abi.check(rc)
+    comm = C.c_void_p()
+    abi.check(lib.rtx_comm_create(ctx.h, 1, 0, C.byref(ident), C.byref(comm)))
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(2))
+    acc = gsc.new_accum(40, 24)
+    gsc.render_into(acc, 0, 8, seed=2)
+    before = acc.clone()
+    abi.check(lib.rtx_accum_reduce(ctx.h, comm, acc.data_ptr(), 40, 24, 0))
+    ctx.sync()
+    import torch
+    assert torch.equal(acc, before)
+    abi.check(lib.rtx_comm_destroy(comm))
+
+
+def test_cli_one_process_per_gpu(tmp_path):
+    """`rttnw --gpus 2`: the parent forks rank 1 before touching CUDA, the ranks render their shares of the sample
+    indices, the parent combines over CUDA IPC. Same image as one GPU (up to fp32 summation order)."""
+    import torch
+    from PIL import Image
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    common = [7, "--spp", 32, "--width", 96, "--height", 96]
+    assert run_cli(common + ["--out", "one.png"], tmp_path).returncode == 0
+    r = run_cli(common + ["--gpus", 2, "--out", "two.png"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    one = np.asarray(Image.open(tmp_path / "one.png")).astype(int)
+    two = np.asarray(Image.open(tmp_path / "two.png")).astype(int)
+    assert np.abs(one - two).max() <= 1

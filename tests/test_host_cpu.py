@@ -182,22 +182,36 @@ def test_shard_spp_partitions_exactly():
 _GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
+import numpy as np
 import torch, torch.distributed as dist
 import rttnw_b200 as R
+from tests import _oracle as O
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
-rank = dist.get_rank()
-begin, count = R.shard_spp(101, rank, 2)
-# stand-in accumulators: what each rank would add for its sample range (sum of sample indices, and the count)
-acc = torch.tensor([float(sum(range(begin, begin + count))), float(count)])
+rank, world = dist.get_rank(), dist.get_world_size()
+# the N > 1 path of bench.py / the CLI with the CPU oracle standing in for the render kernel: every rank builds the
+# same scene from the same seed (rtx_builtin_scene / the oracle's own constructor), renders ITS share of the global
+# sample indices (R.shard_spp) of every pixel, and one sum-reduce to rank 0 is the whole exchange
+W, H, SPP = 24, 16, 13
+osc = O.OracleScene.builtin(7)
+assert R.flatten_check(R.BuiltinDesc(7))["prim_ids"] == osc.prim_count  # both ranks see the same scene
+begin, count = R.shard_spp(SPP, rank, world)
+part, rays = osc.render_sum(W, H, count, seed=5, spp_begin=begin, max_depth=4, threads=2)
+acc = torch.from_numpy(np.concatenate([part, np.full((H, W, 1), float(count))], axis=2))
 dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
 if rank == 0:
-    assert acc.tolist() == [float(sum(range(101))), 101.0], acc
+    whole, _ = osc.render_sum(W, H, SPP, seed=5, max_depth=4, threads=2)
+    got = acc.numpy()
+    assert (got[..., 3] == SPP).all()
+    assert np.allclose(got[..., :3], whole, rtol=1e-12, atol=1e-12), np.abs(got[..., :3] - whole).max()
+    assert np.array_equal(osc.tonemap(got[..., :3].copy(), SPP), osc.tonemap(whole, SPP))
     print("OK")
 dist.destroy_process_group()
 """
 
 
 def test_spp_sharding_reduce_world_size_2_gloo(tmp_path):
+    """Two ranks over gloo: the sharded render (shard_spp over global sample indices + one sum-reduce) equals the
+    single-rank render of the same frame, pixel for pixel."""
     import socket
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -207,29 +221,40 @@ def test_spp_sharding_reduce_world_size_2_gloo(tmp_path):
     script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
     procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
              for r in range(2)]
-    outs = [p.communicate(timeout=120) for p in procs]
+    outs = [p.communicate(timeout=300) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert b"OK" in outs[0][0]
 
 
-def test_committed_profile_counters_feed_the_bench_line():
-    """bench.py quotes ncu counters from profiles/dram_traffic.json (roofline.traffic / .ncu / .issue): the keys it
-    reads must be there, and the issue-slot estimate must come out of them without a GPU."""
+def test_ncu_counters_feed_the_bench_line(tmp_path):
+    """bench.py turns per-sample ncu counters (tools/r2_counters.py) into live roofline fractions, and refuses
+    counters that were captured on other kernel sources."""
     import json
     import bench
-    ncu = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-    for k in ("wf_trace_kernel", "wf_shade_kernel"):
-        for suffix in ("_dram_bytes_per_launch", "_warp_instructions", "_duration_us_alone", "_duration_us_mean_over_a_render",
-                       "_lanes_active_per_warp_instruction"):
-            assert ncu[k + suffix] > 0, k + suffix
-    import torch
+    doc = {"kernels_sha": bench.kernels_sha(), "source": "test", "kernels": {
+        "wf_trace_kernel": {"warp_instructions_per_sample": 820.0, "lanes_per_warp_instruction": 7.9, "dram_bytes_per_sample": 300.0,
+                            "dram_bytes_per_launch": 1.9e7, "l2_bytes_per_sample": 2000.0, "instructions_per_active_sm_cycle": 2.3},
+        "wf_shade2_kernel": {"warp_instructions_per_sample": 480.0, "lanes_per_warp_instruction": 13.7, "dram_bytes_per_sample": 500.0,
+                             "dram_bytes_per_launch": 3e7, "l2_bytes_per_sample": 3000.0, "instructions_per_active_sm_cycle": 1.6}}}
+    r = bench.issue_roof(doc, 600e6, {"sm_mhz": 1965.0}, 148)
+    assert abs(r["peak"] - 4 * 148 * 1.965) < 1e-6 and abs(r["achieved"] - 1300 * 0.6) < 1e-6 and 0.5 < r["frac"] < 0.8
+    assert abs(r["kernels"]["wf_trace_kernel"]["warp_execution_efficiency"] - 7.9 / 32) < 1e-9
+    committed, why = bench.load_counters(9)
+    if committed is None:
+        assert "no counters" in why or "re-run" in why
+    else:
+        assert committed["kernels_sha"] == bench.kernels_sha()
+        assert any(k.startswith("wf_trace") for k in committed["kernels"]) and any(k.startswith("wf_shade") for k in committed["kernels"])
 
-    class Props:
-        multi_processor_count = 148
-    real = torch.cuda.get_device_properties
-    torch.cuda.get_device_properties = lambda i: Props()
-    try:
-        r = bench.issue_roof(ncu, 1968.5, 136.5, {"sm_mhz": 1965.0}, {})
-    finally:
-        torch.cuda.get_device_properties = real
-    assert 0.3 < r["frac"] < 1.0, r
+
+def test_bench_arms_print_the_same_config():
+    """The driver compares the two arms' `config` dicts: they must be equal for the same arguments."""
+    import bench
+    args = bench.parse.__wrapped__() if hasattr(bench.parse, "__wrapped__") else None
+    import argparse
+    ns = argparse.Namespace(scene=9, spp=128, width=0, height=0)
+    d, w, h = bench.workload(ns)
+    assert bench.config(ns, d, w, h) == bench.config(ns, d, w, h)
+    assert set(bench.config(ns, d, w, h)) == {"workload", "scene", "width", "height", "spp_per_gpu_per_step", "max_depth", "sharding", "l2"}
+    for number in range(1, 10):
+        assert bench.scene_defaults(number) == R.scene_defaults(number)  # bench.py's copy of the scene table
