@@ -295,7 +295,14 @@ class Frame:
         self.all_acc = self.root_rgba = self.peers = self.comm = None
         if world == 1:
             return
-        if self.combine in ("auto", "peer", "slice"):
+        if self.combine == "auto":
+            # NCCL behind the C ABI unless the host has no libnccl: measured 30-34 us per 800x800 combine at 2 / 4 / 8 GPUs
+            # against 76-169 us (peer) and 84-127 us (slice) with their two host barriers (profiles/r2_combine_ab.json)
+            probe = (C.c_uint8 * 128)()
+            have = torch.tensor([1.0 if lib.rtx_comm_unique_id(C.byref(probe)) == 0 else 0.0], device=dev)
+            dist.all_reduce(have, op=dist.ReduceOp.MIN)
+            self.combine = "nccl" if have.item() > 0 else "peer"
+        if self.combine in ("peer", "slice"):
             try:
                 def export(ptr):
                     hd = (C.c_uint8 * 64)()
@@ -315,15 +322,11 @@ class Frame:
                 self.root_rgba = self.rgba_p.value if rank == 0 else open_(handles[0][1])
                 ok = torch.ones(1, device=dev)
             except Exception as e:  # noqa: BLE001
-                if self.combine != "auto":
-                    raise
                 sys.stderr.write(f"[rank {rank}] CUDA IPC unavailable ({e}); combining with NCCL\n")
                 ok = torch.zeros(1, device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() <= 0:
                 self.combine = "nccl"
-            elif self.combine == "auto":
-                self.combine = "peer"
         if self.combine == "nccl":
             ident = (C.c_uint8 * 128)()
             if rank == 0:

@@ -8,11 +8,16 @@
 // next sample index it would render to PATH.<gpu>; --resume reloads them (same scene, size, spp, seed, gpus)
 // and carries on. Samples are keyed by their global index, so a resumed image equals an uninterrupted one up
 // to fp32 summation order.
-// With --gpus N the samples are sharded by global sample index, one PROCESS per device: the parent forks ranks 1..N-1
-// before it touches CUDA and renders rank 0's share itself, so the N CUDA contexts come up side by side (in one
-// process the driver creates them one after the other: 7.5 s of a 9 s run for eight devices, round 1). Each child
-// hands the parent the CUDA-IPC handle of its accumulator through a pipe and waits; the parent's fused reduce + tonemap
-// kernel reads them over NVLink. RTTNW_SINGLE_PROCESS=1 keeps everything in one process, one thread per device.
+// With --gpus N the samples are sharded by global sample index, one PROCESS per device, each seeing ONLY its device
+// (CUDA_VISIBLE_DEVICES is narrowed before the process touches CUDA): on an 8-GPU box the CUDA runtime takes 6-7 s to
+// initialise when it can see every device, whether one context is created or eight, in one process or in eight
+// (profiles/r2_multi_gpu_8.txt) — that, not the render, was 7.5 s of round 1's 9 s. The parent forks ranks 1..N-1
+// before it touches CUDA and renders rank 0's share itself. Processes that cannot see each other's devices cannot map
+// each other's memory, so the end-of-frame combine goes through the host: every child copies its accumulator (10 MB at
+// 800x800) into a shared mapping and exits; the parent uploads them and runs the same fused sum + tonemap kernel on local
+// copies (a few milliseconds per frame). RTTNW_SINGLE_PROCESS=1 keeps one process with a thread per device and the
+// peer-mapped combine over NVLink; the NCCL combine (rtx_comm_*, rtx_accum_reduce) is what bench.py uses across ranks.
+#include <sys/mman.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -76,6 +81,24 @@ static bool read_checkpoint(const std::string& path, CheckpointHeader& h, std::v
     return ok;
 }
 
+// Narrows CUDA_VISIBLE_DEVICES to the `rank`-th device this process could see (the rank-th entry of the variable when the
+// user set one, else device `rank`). Must run before the first CUDA call of the process; the device is then number 0.
+static void see_only_device(int rank) {
+    std::string pick = std::to_string(rank);
+    if (const char* cur = std::getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string list = cur;
+        size_t pos = 0;
+        for (int i = 0; i < rank && pos != std::string::npos; ++i) {
+            pos = list.find(',', pos);
+            if (pos != std::string::npos) ++pos;
+        }
+        if (pos == std::string::npos || pos >= list.size()) return;  // fewer entries than ranks: leave it, rtx_ctx_create will say so
+        size_t end = list.find(',', pos);
+        pick = list.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+    }
+    setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
+}
+
 int main(int argc, char** argv) {
     int scene = -1, spp = -1, width = -1, height = -1, gpus = 1, chunk = 256, ckpt_every = 1, stop_after = -1;
     std::string ckpt_path, resume_path;
@@ -130,11 +153,12 @@ int main(int argc, char** argv) {
         if (verbose) std::fprintf(stderr, "[%8.3f s] %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
     };
     lap("scene description built");
+    const bool one_device_per_process = std::getenv("RTTNW_SINGLE_PROCESS") == nullptr;
     std::vector<Rank> ranks((size_t)gpus);
     auto worker = [&](int r) {
         Rank& k = ranks[(size_t)r];
         auto chk = [&](int rc) { if (rc != RTX_OK && k.rc == 0) { k.rc = rc; std::fprintf(stderr, "gpu %d: %s\n", r, rtx_last_error()); } return rc == RTX_OK; };
-        if (!chk(rtx_ctx_create(r, nullptr, &k.ctx))) return;
+        if (!chk(rtx_ctx_create(one_device_per_process ? 0 : r, nullptr, &k.ctx))) return;
         if (r == 0) lap("context created");
         if (!chk(rtx_scene_create(k.ctx, desc, &k.scene))) return;
         if (r == 0) lap("scene uploaded");
@@ -184,96 +208,80 @@ int main(int argc, char** argv) {
         chk(rtx_ctx_sync(k.ctx));
         if (r == 0) lap("render finished");
     };
-    const bool multi_process = gpus > 1 && std::getenv("RTTNW_SINGLE_PROCESS") == nullptr;
-    struct Child {
-        pid_t pid = -1;
-        int up = -1, down = -1;  // child -> parent: status + IPC handle; parent -> child: release
-    };
-    struct UpMsg {
-        int32_t rc;
-        uint8_t handle[64];
-    };
-    std::vector<Child> children;
+    const bool multi_process = gpus > 1 && one_device_per_process;
     std::vector<const float*> peers;
+    if (!multi_process && one_device_per_process) see_only_device(0);
     if (multi_process) {
+        const size_t frame_bytes = (size_t)width * height * 4 * sizeof(float);
+        // one slot per child for its accumulator, shared with the parent; a pipe per child for its status
+        float* shared = (float*)mmap(nullptr, frame_bytes * (size_t)(gpus - 1), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+        if (shared == MAP_FAILED) { std::perror("mmap"); return 1; }
+        struct Child {
+            pid_t pid = -1;
+            int up = -1;
+        };
+        std::vector<Child> children;
         std::fflush(stdout);
         std::fflush(stderr);
         for (int r = 1; r < gpus; ++r) {
-            int up[2], down[2];
-            if (pipe(up) != 0 || pipe(down) != 0) { std::perror("pipe"); return 1; }
+            int up[2];
+            if (pipe(up) != 0) { std::perror("pipe"); return 1; }
             pid_t pid = fork();
             if (pid < 0) { std::perror("fork"); return 1; }
-            if (pid == 0) {  // rank r: render, publish the accumulator, wait until the parent has read it
+            if (pid == 0) {  // rank r: sees its device only, renders its share, leaves the accumulator in the shared mapping
                 close(up[0]);
-                close(down[1]);
+                see_only_device(r);
                 worker(r);
                 Rank& k = ranks[(size_t)r];
-                UpMsg msg;
-                std::memset(&msg, 0, sizeof(msg));
-                msg.rc = k.rc;
-                if (k.rc == 0 && rtx_ipc_export(k.ctx, k.accum, msg.handle) != RTX_OK) {
+                int32_t rc = k.rc;
+                if (rc == 0 && rtx_memcpy_d2h(k.ctx, (char*)shared + frame_bytes * (size_t)(r - 1), k.accum, frame_bytes) != RTX_OK) {
                     std::fprintf(stderr, "gpu %d: %s\n", r, rtx_last_error());
-                    msg.rc = 1;
+                    rc = 1;
                 }
-                ssize_t w = write(up[1], &msg, sizeof(msg));
-                char go = 0;
-                if (w == (ssize_t)sizeof(msg) && msg.rc == 0) { ssize_t g = read(down[0], &go, 1); (void)g; }
-                if (k.accum) rtx_free(k.ctx, k.accum);
-                if (k.scene) rtx_scene_destroy(k.scene);
-                if (k.ctx) rtx_ctx_destroy(k.ctx);
-                _exit(msg.rc);
+                ssize_t w = write(up[1], &rc, sizeof(rc));
+                (void)w;
+                _exit(rc == 0 ? 0 : (rc == 3 ? 3 : 1));  // (no teardown: the process ends here and the driver reclaims the device)
             }
             close(up[1]);
-            close(down[0]);
             Child c;
-            c.pid = pid; c.up = up[0]; c.down = down[1];
+            c.pid = pid; c.up = up[0];
             children.push_back(c);
         }
+        see_only_device(0);
         worker(0);
         int bad = ranks[0].rc;
-        std::vector<void*> opened;
         for (size_t i = 0; i < children.size(); ++i) {
-            UpMsg msg;
-            ssize_t got = read(children[i].up, &msg, sizeof(msg));
-            if (got != (ssize_t)sizeof(msg)) { msg.rc = 1; std::fprintf(stderr, "gpu %zu: worker process died\n", i + 1); }
-            if (msg.rc != 0 && bad == 0) bad = msg.rc;
-            if (msg.rc == 0 && bad == 0) {
-                void* p = nullptr;
-                if (rtx_ipc_open(ranks[0].ctx, msg.handle, &p) != RTX_OK) { std::fprintf(stderr, "rtx_ipc_open: %s\n", rtx_last_error()); bad = 1; }
-                else { opened.push_back(p); peers.push_back((const float*)p); }
-            }
+            int32_t rc = 1;
+            if (read(children[i].up, &rc, sizeof(rc)) != (ssize_t)sizeof(rc)) { rc = 1; std::fprintf(stderr, "gpu %zu: worker process died\n", i + 1); }
+            close(children[i].up);
+            if (rc != 0 && bad == 0) bad = rc;
         }
-        auto release_children = [&]() {
-            for (auto& c : children) {
-                char go = 1;
-                ssize_t w = write(c.down, &go, 1);
-                (void)w;
-                close(c.down);
-                close(c.up);
-                int status = 0;
-                waitpid(c.pid, &status, 0);
-            }
-        };
-        if (bad != 0) { release_children(); return bad == 3 ? 3 : 1; }
+        if (bad != 0) {
+            for (auto& c : children) { int st = 0; waitpid(c.pid, &st, 0); }
+            return bad == 3 ? 3 : 1;
+        }
         lap("all ranks finished");
+        std::vector<void*> staged;
+        for (int r = 1; r < gpus; ++r) {
+            void* d = nullptr;
+            RTX(rtx_malloc(ranks[0].ctx, frame_bytes, &d));
+            RTX(rtx_memcpy_h2d(ranks[0].ctx, d, (char*)shared + frame_bytes * (size_t)(r - 1), frame_bytes));
+            staged.push_back(d);
+            peers.push_back((const float*)d);
+        }
         std::vector<uint8_t> rgba_mp((size_t)width * height * 4);
         uint8_t* d_rgba_mp = nullptr;
         RTX(rtx_malloc(ranks[0].ctx, rgba_mp.size(), (void**)&d_rgba_mp));
-        RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.empty() ? nullptr : peers.data(), (int)peers.size(), width, height, d_rgba_mp));
+        RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.data(), (int)peers.size(), width, height, d_rgba_mp));
         RTX(rtx_memcpy_d2h(ranks[0].ctx, rgba_mp.data(), d_rgba_mp, rgba_mp.size()));
         lap("frame on the host");
-        for (void* p : opened) rtx_ipc_close(ranks[0].ctx, p);
-        release_children();
         RTX(rtx_png_write_rgba8(out.c_str(), width, height, rgba_mp.data()));
         lap("png written");
-        rtx_free(ranks[0].ctx, d_rgba_mp);
-        rtx_free(ranks[0].ctx, ranks[0].accum);
-        rtx_scene_destroy(ranks[0].scene);
-        rtx_ctx_destroy(ranks[0].ctx);
-        rtx_scene_desc_free(desc);
         double secs_mp = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::printf("%.6fs\n", secs_mp);  // println!("{:?}", instant.elapsed())
-        return 0;
+        std::fflush(stdout);
+        for (auto& c : children) { int st = 0; waitpid(c.pid, &st, 0); }
+        _exit(0);  // like the children: no context teardown at the end of the process
     }
     std::vector<std::thread> th;
     for (int r = 0; r < gpus; ++r) th.emplace_back(worker, r);

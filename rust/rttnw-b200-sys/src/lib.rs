@@ -7,8 +7,17 @@
 //! save, CLI) stays as it is. INTEGRATION.md shows the three edits inside the reference's tree:
 //! one `describe` method per trait, `BvhTree` remembering its list, and the new `render()` body.
 //!
+//! Modules: `ffi` (raw bindings), `math` (the reference's scene API as description-only types: every `Hittable`,
+//! `Material` and `Texture` of src/math/*.rs with a `describe` method), `scenes` (the reference's own scenes.rs,
+//! included and compiled against `math`), `render` (the scene table and `render()`).
+//!
 //! NOT BUILT in this repository's image (no Rust toolchain): reviewed source only.
 pub mod ffi;
+pub mod math;
+pub mod render;
+pub mod scenes;
+
+pub use render::{render, render_world, scene_setup, shard_spp};
 
 use std::collections::HashMap;
 use std::ffi::CStr;
@@ -22,7 +31,7 @@ pub struct RtxError {
     pub message: String,
 }
 
-fn check(status: i32) -> Result<(), RtxError> {
+pub(crate) fn check(status: i32) -> Result<(), RtxError> {
     if status == ffi::RTX_OK {
         return Ok(());
     }
@@ -141,18 +150,29 @@ impl Gpu {
             images: images.as_ptr(), n_images: images.len() as i32, _pad: 0,
             background, camera,
         };
+        self.render_desc(&desc, width, height, samples, seed)
+    }
+
+    /// The same for a ready-made description (e.g. `rtx_builtin_scene`).
+    pub fn render_desc(&self, desc: *const ffi::rtx_scene_desc, width: u32, height: u32, samples: usize, seed: u64) -> Result<Vec<u8>, RtxError> {
         let bytes = width as usize * height as usize * 16;
         let mut pixels = vec![0u8; width as usize * height as usize * 4];
         unsafe {
             let mut scene = ptr::null_mut();
-            check(ffi::rtx_scene_create(self.ctx, &desc, &mut scene))?;
+            check(ffi::rtx_scene_create(self.ctx, desc, &mut scene))?;
             let mut accum: *mut c_void = ptr::null_mut();
             let result = (|| {
                 check(ffi::rtx_malloc(self.ctx, bytes, &mut accum))?;
                 check(ffi::rtx_memset_zero(self.ctx, accum, bytes))?;
-                let params = ffi::rtx_render_params { width: width as i32, height: height as i32, spp_begin: 0,
-                                                      spp_count: samples as i32, max_depth: 50, _pad: 0, seed };
-                check(ffi::rtx_render(self.ctx, scene, &params, accum as *mut f32, ptr::null_mut()))?;
+                // rtx_render takes at most 2^26 samples per pixel per call: a frame is rendered in chunks of sample indices
+                let mut begin = 0usize;
+                while begin < samples {
+                    let count = (samples - begin).min(1 << 20);
+                    let params = ffi::rtx_render_params { width: width as i32, height: height as i32, spp_begin: begin as i32,
+                                                          spp_count: count as i32, max_depth: 50, _pad: 0, seed };
+                    check(ffi::rtx_render(self.ctx, scene, &params, accum as *mut f32, ptr::null_mut()))?;
+                    begin += count;
+                }
                 check(ffi::rtx_tonemap_rgba8(self.ctx, accum as *const f32, width as i32, height as i32, pixels.as_mut_ptr(), 0))
             })();
             if !accum.is_null() {
