@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
     ap.add_argument("--no-frames", action="store_true", help="skip the final_10k / Cornell frames")
+    ap.add_argument("--big-scene", type=int, default=2_000_000, help="spheres of the out-of-cache closest-hit leg at N=1 (0: skip)")
     ap.add_argument("--final-spp", type=int, default=10000, help="total spp of the final_10k frame (the reference default)")
     ap.add_argument("--cornell-spp", type=int, default=8000, help="total spp of the Cornell frames (reference default 200: too short to time)")
     return ap.parse_args()
@@ -268,6 +269,81 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def big_scene_leg(R, abi, ctx, n_prims, n_rays, hbm_peak, l2_gbs):
+    """The closest-hit kernel outside the cache-resident regime the shipped scenes live in (their flattened form is
+    0.5 MB): n_prims random spheres — a BVH + record set several times the 126 MB L2 — built by the device LBVH builder,
+    traced by rtx_trace_rays_device with uniformly random rays through the volume (the least coherent case). Reported
+    with its own roofline: here HBM bandwidth is a roof that means something."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(5)
+    side = n_prims ** (1.0 / 3.0) * 3.0
+    node_dt = np.dtype([("kind", "<i4"), ("material", "<i4"), ("child", "<i4"), ("n_children", "<i4"), ("f", "<f8", 10)])
+    assert node_dt.itemsize == C.sizeof(abi.Node)
+    nodes = np.zeros(n_prims + 1, dtype=node_dt)
+    nodes["kind"][:n_prims] = abi.NODE_SPHERE
+    nodes["child"][:n_prims] = -1
+    nodes["f"][:n_prims, :3] = rng.uniform(-side, side, (n_prims, 3))
+    nodes["f"][:n_prims, 3] = rng.uniform(0.2, 1.0, n_prims)
+    nodes[n_prims] = (abi.NODE_LIST, -1, 0, n_prims, np.zeros(10))
+    children = np.arange(n_prims, dtype=np.int32)
+    mat, tex = abi.Material(), abi.Texture()
+    mat.kind, mat.texture = abi.MAT_LAMBERTIAN, 0
+    tex.kind = abi.TEX_SOLID
+    tex.f[0] = tex.f[1] = tex.f[2] = 0.5
+    desc = abi.SceneDesc()
+    desc.nodes = nodes.ctypes.data_as(C.POINTER(abi.Node))
+    desc.n_nodes, desc.root = n_prims + 1, n_prims
+    desc.children = children.ctypes.data_as(C.POINTER(C.c_int32))
+    desc.n_children = n_prims
+    desc.materials, desc.n_materials = C.pointer(mat), 1
+    desc.textures, desc.n_textures = C.pointer(tex), 1
+    cam = desc.camera
+    cam.lookfrom[0], cam.lookfrom[1], cam.lookfrom[2] = 0.0, 0.0, -3.0 * side
+    cam.view_up[1] = 1.0
+    cam.vertical_fov, cam.aspect_ratio, cam.focus_distance, cam.close_time = 40.0, 1.0, 10.0, 1.0
+    ctx.set_bvh_builder("lbvh")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sc = R.DeviceScene(ctx, desc)
+    torch.cuda.synchronize()
+    create_s = time.perf_counter() - t0
+    ctx.set_bvh_builder("sah")
+    o, tgt = rng.uniform(-side, side, (n_rays, 3)), rng.uniform(-side, side, (n_rays, 3))
+    rays = np.zeros(n_rays, dtype=abi.RAY_DTYPE)
+    rays["origin"], rays["direction"] = o, tgt - o
+    rays["t_min"], rays["t_max"], rays["xi"] = 0.001, np.finfo(np.float64).max, 0.5
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(n_rays * 88, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        sc.trace_device(d_rays, d_hits, n_rays)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        sc.trace_device(d_rays, d_hits, n_rays)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    st = sc.trace_stats(d_rays, n_rays)
+    info = sc.info()
+    hits = d_hits.cpu().numpy().view(abi.HIT_DTYPE)
+    # bytes a ray must fetch: 32 per child box tested + 96 per primitive record tested (f64 records), + its own 80 in / 88 out
+    a_ray = 32.0 * st["box_tests"] + 96.0 * (st["sphere_tests"] + st["rect_tests"]) + 168.0
+    gbs = a_ray * n_rays / (ms * 1e-3) / 1e9
+    sc.close()
+    return {"primitives": n_prims, "bvh": "device LBVH (Morton codes + radix sort + Karras)", "bvh_nodes": info["bvh_nodes"],
+            "scene_bytes": info["device_bytes"], "scene_create_s": create_s, "rays": n_rays, "ms_per_launch": ms,
+            "rays_per_sec": n_rays / (ms * 1e-3), "hit_fraction": float(np.mean(hits["prim_id"] >= 0)),
+            "per_ray_means": {k: st[k] for k in ("box_tests", "node_visits", "sphere_tests")},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_ray": a_ray, "l2_frac": gbs / l2_gbs,
+                         "note": "algorithmic bytes (node pairs 64 B per visit, records 96 B per test, the ray and its hit) against the "
+                                 "measured HBM copy bandwidth; the working set is %.0f MB against 126 MB of L2, the rays are incoherent, "
+                                 "so a node visit is a dependent, mostly-missing 64-byte fetch: latency, not bandwidth, is what is left "
+                                 "between this fraction and 1" % (info["device_bytes"] / 1e6)}}
+
+
 class Frame:
     """One accumulator + RGBA8 frame of a given size on this rank, with the multi-GPU combine wired up:
       peer  : rank 0's fused reduce + tonemap kernel reads the other accumulators over NVLink (CUDA-IPC mappings)
@@ -610,6 +686,11 @@ def run_ours(args):
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
                 "frames": frames,
                 "roofline": roofline}
+        if world == 1 and args.big_scene > 0:
+            try:
+                line["big_scene"] = big_scene_leg(R, abi, ctx, args.big_scene, 4_000_000, hbm_peak, l2_gbs)
+            except Exception as e:  # noqa: BLE001 (an out-of-memory box must not lose the headline)
+                line["big_scene"] = {"unavailable": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
     if world > 1:

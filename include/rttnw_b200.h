@@ -169,7 +169,10 @@ typedef struct rtx_scene_desc {
 typedef struct rtx_ray {
     double origin[3];
     double direction[3]; /* not normalised (Ray.b, src/math/ray.rs:9-13) */
-    double time;
+    double time;         /* must lie in [min(0, camera.open_time), max(1, camera.close_time)]: the BVH bounds of a
+                            MovingSphere cover its positions over that interval only (the reference's BvhTree::from uses
+                            [0, 1], hittable.rs:255-258), so a ray outside it may miss a moving sphere it would hit in a
+                            flat List. Render rays always comply (Camera::ray draws the time inside the shutter). */
     double t_min;
     double t_max;
     double xi; /* the uniform variate ConstantMedium::hit draws (hittable.rs:765) */
@@ -228,6 +231,16 @@ int rtx_device_count(int* count);
 int rtx_ctx_create(int device, void* stream, rtx_ctx** out);
 int rtx_ctx_destroy(rtx_ctx* ctx);
 int rtx_ctx_sync(rtx_ctx* ctx);
+/* Asynchronous rendering (off by default). The wavefront driver behind rtx_render feeds the stream in batches and
+ * watches a completion counter, which keeps the calling thread busy for the length of the render. With on != 0 that
+ * loop runs on a thread the context owns: rtx_render queues the job and returns at once (the parameter struct is
+ * copied; scene and accumulator must stay alive), so one host thread can keep several GPUs rendering. Every other
+ * entry point taking this ctx — rtx_ctx_sync above all — first waits for that thread to run dry, which keeps the
+ * calls of ONE context in program order; an asynchronous render that failed reports its error from the next such
+ * call. Work the caller puts on the ctx stream BEHIND the ABI's back (e.g. torch ops on a shared stream) is not
+ * ordered against a queued render: call rtx_ctx_sync first. Destroy a scene only after syncing the contexts that
+ * render it. */
+int rtx_ctx_set_async(rtx_ctx* ctx, int on);
 void* rtx_ctx_stream(rtx_ctx* ctx);
 /* Which builder makes the BVH over the world in rtx_scene_create (replaces BvhTree::new, hittable.rs:260-321; the
  * tree's topology is not part of the contract, only the closest-hit answers): 0 = host, binned SAH (default, the
@@ -251,6 +264,9 @@ int rtx_ctx_measure_l2_read(rtx_ctx* ctx, unsigned long long bytes, int repeats,
  * copied; the caller keeps ownership of everything in `desc`). ---- */
 int rtx_scene_create(rtx_ctx* ctx, const rtx_scene_desc* desc, rtx_scene** out);
 int rtx_scene_destroy(rtx_scene* scene);
+/* rtx_scene_destroy keeps up to four device arenas / texture arrays per device for the next rtx_scene_create (a host
+ * that re-uploads its scene every frame then pays two copies instead of cudaMalloc + cudaFree): this frees them. */
+int rtx_cache_trim(int device);
 /* sizes of the flattened device representation (for roofline bookkeeping) */
 int rtx_scene_info(const rtx_scene* scene, int32_t* n_bvh_nodes, int32_t* n_records,
                    int32_t* n_xform_ops, int64_t* device_bytes);
@@ -270,12 +286,19 @@ int rtx_trace_rays_stats(rtx_ctx* ctx, const rtx_scene* scene, int64_t n, const 
 /* Adds spp_count samples per pixel into d_accum (device, width*height float4:
  * sum r, sum g, sum b, sample count; row 0 = TOP row, matching the order the
  * reference emits pixels, src/main.rs:202-204). All work is ordered on the ctx
- * stream and the result is NOT synchronised on return; the call itself may keep
+ * stream and the result is NOT synchronised on return. By default the call keeps
  * the calling thread busy while it feeds the stream (the wavefront driver polls
- * a completion counter). Samples are added with atomics: the fp32 summation
+ * a completion counter); after rtx_ctx_set_async(ctx, 1) it returns at once. Samples are added with atomics: the fp32 summation
  * order, hence the last bits of the sums, can differ from run to run.
  * d_ray_count (device uint64, may be NULL) is incremented by the number of
- * world.hit queries issued. */
+ * world.hit queries issued. The sample count of a pixel is kept in the fp32 .w of
+ * the accumulator: at most 2^24 samples per pixel can be accumulated in one
+ * buffer (16.7 M; the reference's largest default is 10^4), and at most 2^24 per
+ * call. Uniform variates are 24-bit (word >> 8) / 2^24: exact in fp32 and f64
+ * alike, which is what makes accept / reject decisions identical to the
+ * oracle's; a ConstantMedium therefore never samples a free flight longer than
+ * 24 ln 2 / density (16.6 mean free paths), where the reference's 53-bit draws
+ * reach 36.7. */
 int rtx_render(rtx_ctx* ctx, const rtx_scene* scene, const rtx_render_params* params,
                float* d_accum, unsigned long long* d_ray_count);
 /* Same render through the counting build of the kernel (slower; for roofline bookkeeping):

@@ -109,6 +109,7 @@ SIGNATURES = {
     "rtx_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "rtx_ctx_destroy": (C.c_int, [_P]),
     "rtx_ctx_sync": (C.c_int, [_P]),
+    "rtx_ctx_set_async": (C.c_int, [_P, C.c_int]),
     "rtx_ctx_stream": (_P, [_P]),
     "rtx_ctx_set_bvh_builder": (C.c_int, [_P, C.c_int]),
     "rtx_ctx_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
@@ -117,6 +118,7 @@ SIGNATURES = {
     "rtx_ctx_measure_l2_read": (C.c_int, [_P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "rtx_scene_create": (C.c_int, [_P, C.POINTER(SceneDesc), C.POINTER(_P)]),
     "rtx_scene_destroy": (C.c_int, [_P]),
+    "rtx_cache_trim": (C.c_int, [C.c_int]),
     "rtx_scene_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int64)]),
     "rtx_trace_rays": (C.c_int, [_P, _P, C.c_int64, _P, _P]),

@@ -8,6 +8,10 @@
 #include <cstring>
 #include <mutex>
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -91,9 +95,11 @@ struct rtx_ctx {
     // loads (trace2.cuh, "1c"; 596 M). Forms 2-4 need a world BVH no deeper than kShortStack and fall back to 1.
     int trace_form = 1;
     int trace_threads = 896;               // CTA size of the shared-memory form, one CTA per SM (RTX_TRACE_THREADS: 896, 640, 512, 448)
-    int t_leaf = 33, t_refill = 33, t_burst = 1 << 30;  // its vote thresholds (RTX_T_LEAF / RTX_T_REFILL / RTX_T_BURST)
+    int t_leaf = 8, t_refill = 16, t_burst = 8;  // its vote thresholds (RTX_T_LEAF / RTX_T_REFILL / RTX_T_BURST); 33 / 33 / huge = plain while-while
     int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int prof_stride = 8;                   // RTX_PROF_STRIDE: every n-th iteration of partition 0 is bracketed when profiling is on
+    bool perlin_smem = true;               // the shade kernel stages the Perlin table (noise.rs:5-29) in shared memory when the scene has exactly one
+                                           // (RTX_PERLIN_SMEM=0 reads it through L1: measured 3.4 % / 1 % / 0.3 % slower on scenes 3 / 5 / 9)
     bool debug_batches = false;            // RTX_DEBUG_BATCHES=1: one stderr line per batch and partition
     int shade_form = 2;                    // RTX_SHADE: 2 = media after the surface search + early dispenser request (shade2.cuh), 1 = first form
     std::vector<cudaStream_t> aux_streams;
@@ -110,6 +116,17 @@ struct rtx_ctx {
     double prof_shade_ms = 0, prof_trace_ms = 0;
     unsigned long long prof_iterations = 0;
     int w_node = 1, w_leaf = 1, w_shade = 1;  // render_kernel phase weights (RTX_W_NODE / RTX_W_LEAF / RTX_W_SHADE override)
+    // rtx_ctx_set_async: rtx_render hands the wavefront driver's submit-and-poll loop to this context's own thread and
+    // returns at once; every other entry point that uses the context first waits for that thread to run dry
+    bool async = false;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<int()>> jobs;
+    int jobs_open = 0;  // queued + running
+    bool stop = false;
+    int async_rc = RTX_OK;  // first failure of a job, reported by the next call that joins
+    std::string async_err;
 };
 
 struct rtx_scene {
@@ -121,7 +138,49 @@ struct rtx_scene {
     std::vector<ArraySlot> images;
     int32_t n_nodes = 0, n_records = 0, n_xforms = 0;
     int32_t world_first_node = 0, world_node_count = 0, world_depth = 0;  // the world BVH's node range (root first) and depth
+    int32_t n_perlins = 0;
 };
+
+// Waits until the context's worker thread has nothing queued or running; returns (once) the failure of an asynchronous
+// render, if there was one. Called at the top of every entry point that uses the context's stream or state.
+static int join_async(rtx_ctx* c) {
+    if (!c || !c->worker.joinable()) return RTX_OK;
+    std::unique_lock<std::mutex> lock(c->mu);
+    c->cv.wait(lock, [&] { return c->jobs_open == 0; });
+    if (c->async_rc != RTX_OK) {
+        int rc = c->async_rc;
+        g_err = c->async_err;
+        c->async_rc = RTX_OK;
+        return rc;
+    }
+    return RTX_OK;
+}
+#define JOIN(c)                          \
+    do {                                 \
+        int rc__ = join_async(c);        \
+        if (rc__ != RTX_OK) return rc__; \
+    } while (0)
+
+static void worker_main(rtx_ctx* c) {
+    for (;;) {
+        std::function<int()> job;
+        {
+            std::unique_lock<std::mutex> lock(c->mu);
+            c->cv.wait(lock, [&] { return c->stop || !c->jobs.empty(); });
+            if (c->jobs.empty()) return;  // stop requested and nothing left
+            job = std::move(c->jobs.front());
+            c->jobs.pop_front();
+        }
+        g_err.clear();
+        int rc = job();
+        {
+            std::lock_guard<std::mutex> lock(c->mu);
+            if (rc != RTX_OK && c->async_rc == RTX_OK) { c->async_rc = rc; c->async_err = g_err; }
+            --c->jobs_open;
+        }
+        c->cv.notify_all();
+    }
+}
 
 extern "C" {
 
@@ -149,16 +208,16 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
         c->stream = (cudaStream_t)stream;
     } else {
         cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+        if (e != cudaSuccess) { rtx_ctx_destroy(c); return cuda_fail(e, "cudaStreamCreate"); }
         c->own_stream = true;
     }
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaGetDeviceProperties"); }
+    if (e != cudaSuccess) { rtx_ctx_destroy(c); return cuda_fail(e, "cudaGetDeviceProperties"); }
     c->sm_count = prop.multiProcessorCount;
     e = cudaMalloc(&c->d_work_counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(rtx::Counters));
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc"); }
+    if (e != cudaSuccess) { rtx_ctx_destroy(c); return cuda_fail(e, "cudaMalloc"); }
     auto env_int = [](const char* name, int dflt) {
         const char* v = std::getenv(name);
         int x = v ? std::atoi(v) : dflt;
@@ -179,6 +238,7 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->t_burst = env_int("RTX_T_BURST", c->t_burst);
     c->shade_form = env_int("RTX_SHADE", c->shade_form);
     c->debug_batches = env_int("RTX_DEBUG_BATCHES", 0) != 0;
+    if (const char* v = std::getenv("RTX_PERLIN_SMEM")) c->perlin_smem = std::atoi(v) != 0;
     c->prof_stride = env_int("RTX_PROF_STRIDE", c->prof_stride);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
@@ -192,8 +252,14 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
 
 int rtx_ctx_destroy(rtx_ctx* c) {
     if (!c) return RTX_OK;
+    if (c->worker.joinable()) {
+        join_async(c);
+        { std::lock_guard<std::mutex> lock(c->mu); c->stop = true; }
+        c->cv.notify_all();
+        c->worker.join();
+    }
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream || !c->own_stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_work_counter);
     cudaFree(c->d_counters);
     cudaFree(c->d_pool);
@@ -212,8 +278,17 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     return RTX_OK;
 }
 
+int rtx_ctx_set_async(rtx_ctx* c, int on) {
+    if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    JOIN(c);
+    c->async = on != 0;
+    if (c->async && !c->worker.joinable()) c->worker = std::thread(worker_main, c);
+    return RTX_OK;
+}
+
 int rtx_ctx_sync(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     return RTX_OK;
@@ -226,6 +301,7 @@ int rtx_ctx_set_profiling(rtx_ctx* c, int on) {
 }
 int rtx_ctx_profile_read(rtx_ctx* c, double* shade_ms, double* trace_ms, unsigned long long* iterations, int reset) {
     if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    JOIN(c);
     if (shade_ms) *shade_ms = c->prof_shade_ms;
     if (trace_ms) *trace_ms = c->prof_trace_ms;
     if (iterations) *iterations = c->prof_iterations;
@@ -287,6 +363,7 @@ int rtx_ctx_kernel_launches(rtx_ctx* c, unsigned long long* out) {
 // ---- scene ----------------------------------------------------------------
 int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     if (!c || !desc || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    JOIN(c);
     *out = nullptr;
     CU(cudaSetDevice(c->device));
     rtx::FlatScene fs;
@@ -464,6 +541,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     s->world_first_node = fs.world_first_node;
     s->world_node_count = fs.world_node_count;
     s->world_depth = fs.world_depth;
+    s->n_perlins = (int32_t)fs.perlins.size();
     *out = s;
     return RTX_OK;
 }
@@ -493,6 +571,19 @@ int rtx_scene_destroy(rtx_scene* s) {
     return RTX_OK;
 }
 
+int rtx_cache_trim(int device) {
+    if (device < 0 || device >= kMaxDevices) return fail(RTX_ERR_INVALID, "no such device slot");
+    DeviceCache& dc = g_cache[device];
+    std::lock_guard<std::mutex> lock(dc.m);
+    if (dc.arenas.empty() && dc.arrays.empty()) return RTX_OK;
+    CU(cudaSetDevice(device));
+    for (auto& a : dc.arenas) cudaFree(a.p);
+    for (auto& im : dc.arrays) { cudaDestroyTextureObject(im.tex); cudaFreeArray(im.arr); }
+    dc.arenas.clear();
+    dc.arrays.clear();
+    return RTX_OK;
+}
+
 int rtx_scene_info(const rtx_scene* s, int32_t* n_bvh_nodes, int32_t* n_records, int32_t* n_xform_ops, int64_t* device_bytes) {
     if (!s) return fail(RTX_ERR_INVALID, "scene is NULL");
     if (n_bvh_nodes) *n_bvh_nodes = s->n_nodes;
@@ -505,6 +596,7 @@ int rtx_scene_info(const rtx_scene* s, int32_t* n_bvh_nodes, int32_t* n_records,
 // ---- fixed rays -------------------------------------------------------------
 int rtx_trace_rays_device(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ray* d_rays, rtx_hit* d_hits) {
     if (!c || !s || n < 0 || (n > 0 && (!d_rays || !d_hits))) return fail(RTX_ERR_INVALID, "bad argument");
+    JOIN(c);
     if (n == 0) return RTX_OK;
     CU(cudaSetDevice(c->device));
     const int block = 128;
@@ -543,6 +635,7 @@ int rtx_trace_rays(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ray* ray
 
 int rtx_trace_rays_stats(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ray* d_rays, rtx_trace_stats* out) {
     if (!c || !s || n <= 0 || !d_rays || !out) return fail(RTX_ERR_INVALID, "bad argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(rtx::Counters), c->stream));
     const int block = 128;
@@ -708,7 +801,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             t3cfg.stage_first = s->world_first_node;
             t3cfg.n_stage = cap;
             t3cfg.cap = cap;
-            t3cfg.burst = c->t_burst > 64 ? 4 : c->t_burst;
+            t3cfg.burst = c->t_burst;
             t3_smem = rtx::trace3_smem_bytes(t3_threads, cap);
             t2_threads = 0;
         }
@@ -799,6 +892,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 CU(prof_mark());
                 if (c->shade_form >= 2) {
                     if (counted) rtx::wf_shade2_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                    else if (c->perlin_smem && s->n_perlins == 1) rtx::wf_shade2_kernel<false, true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
                     else rtx::wf_shade2_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
                 } else {
                     if (counted) rtx::wf_shade_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
@@ -876,7 +970,7 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     if (p->width <= 0 || p->height <= 0 || p->spp_count < 0 || p->spp_begin < 0 || p->max_depth < 0)
         return fail(RTX_ERR_INVALID, "bad render parameters");
     if ((int64_t)p->width * p->height > 0x7fffffff) return fail(RTX_ERR_INVALID, "image too large");
-    if (p->spp_count > (1 << 26)) return fail(RTX_ERR_INVALID, "more than 2^26 samples per pixel in one call");
+    if (p->spp_count > (1 << 24)) return fail(RTX_ERR_INVALID, "more than 2^24 samples per pixel in one call (the fp32 sample count of the accumulator)");
     if (p->spp_count == 0) return RTX_OK;
     CU(cudaSetDevice(c->device));
     if (p->max_depth == 0) {  // color(.., depth = 0) is black (main.rs:27-29): only the sample counts move
@@ -920,11 +1014,22 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
 }
 
 int rtx_render(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum, unsigned long long* d_ray_count) {
+    if (c && c->async && s && p && d_accum) {
+        const rtx_render_params params = *p;  // the caller's struct need not outlive the call
+        {
+            std::lock_guard<std::mutex> lock(c->mu);
+            c->jobs.push_back([=]() { return render_launch(c, s, &params, d_accum, d_ray_count, false); });
+            ++c->jobs_open;
+        }
+        c->cv.notify_all();
+        return RTX_OK;
+    }
     return render_launch(c, s, p, d_accum, d_ray_count, false);
 }
 
 int rtx_render_counted(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* p, float* d_accum, rtx_trace_stats* out) {
     if (!c || !out) return fail(RTX_ERR_INVALID, "NULL argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     unsigned long long* d_rays = nullptr;
     CU(cudaMalloc(&d_rays, sizeof(unsigned long long)));
@@ -954,6 +1059,7 @@ int rtx_render_counted(rtx_ctx* c, const rtx_scene* s, const rtx_render_params* 
 
 int rtx_tonemap_rgba8(rtx_ctx* c, const float* d_accum, int32_t width, int32_t height, uint8_t* out, int out_on_device) {
     if (!c || !d_accum || !out || width <= 0 || height <= 0) return fail(RTX_ERR_INVALID, "bad argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     int n = width * height;
     uchar4* d_out = (uchar4*)out;
@@ -999,6 +1105,7 @@ int rtx_reduce_tonemap_peers(rtx_ctx* c, float* d_accum, const float* const* d_p
     if (!c || !d_accum || !d_rgba8 || width <= 0 || height <= 0 || n_peers < 0 || (n_peers > 0 && !d_peer_accums))
         return fail(RTX_ERR_INVALID, "bad argument");
     if (n_peers > rtx::kMaxPeers) return fail(RTX_ERR_UNSUPPORTED, "too many peers");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     const int n = width * height;
     rtx::PeerList pl;
@@ -1027,6 +1134,7 @@ int rtx_reduce_tonemap_slice(rtx_ctx* c, const float* const* d_accums, int32_t n
     if (!c || !d_accums || !d_rgba8_root || width <= 0 || height <= 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
         return fail(RTX_ERR_INVALID, "bad argument");
     if (n_ranks > rtx::kMaxPeers) return fail(RTX_ERR_UNSUPPORTED, "too many ranks");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     const long long n = (long long)width * height;
     const int first = (int)(n * rank / n_ranks), count = (int)(n * (rank + 1) / n_ranks) - first;
@@ -1135,6 +1243,7 @@ int rtx_comm_destroy(rtx_comm* k) {
 }
 int rtx_accum_reduce(rtx_ctx* c, rtx_comm* k, float* d_accum, int32_t width, int32_t height, int32_t root) {
     if (!c || !k || !k->comm || !d_accum || width <= 0 || height <= 0 || root < 0) return fail(RTX_ERR_INVALID, "bad argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     const size_t count = (size_t)width * (size_t)height * 4;
     int r = nccl().Reduce(d_accum, d_accum, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, root, k->comm, c->stream);
@@ -1151,18 +1260,21 @@ int rtx_malloc(rtx_ctx* c, size_t bytes, void** out) {
 }
 int rtx_free(rtx_ctx* c, void* ptr) {
     if (!c) return fail(RTX_ERR_INVALID, "ctx is NULL");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     CU(cudaFree(ptr));
     return RTX_OK;
 }
 int rtx_memset_zero(rtx_ctx* c, void* ptr, size_t bytes) {
     if (!c || !ptr) return fail(RTX_ERR_INVALID, "NULL argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(ptr, 0, bytes, c->stream));
     return RTX_OK;
 }
 int rtx_memcpy_h2d(rtx_ctx* c, void* dst, const void* src, size_t bytes) {
     if (!c || !dst || !src) return fail(RTX_ERR_INVALID, "NULL argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1170,6 +1282,7 @@ int rtx_memcpy_h2d(rtx_ctx* c, void* dst, const void* src, size_t bytes) {
 }
 int rtx_memcpy_d2h(rtx_ctx* c, void* dst, const void* src, size_t bytes) {
     if (!c || !dst || !src) return fail(RTX_ERR_INVALID, "NULL argument");
+    JOIN(c);
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -163,8 +163,12 @@ __device__ __forceinline__ void to_space(const SceneView& sc, int32_t chain, d3&
 }
 
 // ---------------------------------------------------------------------------
-// Primitive tests: same operations, in the same order, as the reference (f64).
-// They only decide and return t; the hit record is built once, for the winner.
+// Primitive tests in f64, following the reference's formulas. They only decide and return t; the hit record is built
+// once, for the winner. Two deliberate departures, each one rounding away from the reference and far inside the 1e-5
+// contract (largest t error over 9 x 10^7 fixed rays: 1e-7, profiles/r2_parity.json): the sphere roots are multiplied
+// by 1 / a where hittable.rs:97,102 divides by a, and a MovingSphere's centre uses a stored 1 / (t1 - t0). A root that
+// lands within that rounding of t_min / t_max can therefore be accepted on one side and rejected on the other: such
+// rays are what the oracle's grazing-tie flag marks, and ids are compared outside that set.
 // ---------------------------------------------------------------------------
 // Sphere::hit / MovingSphere::hit quadratic, hittable.rs:88-108,196-216 (Q9: both ends inclusive)
 __device__ __forceinline__ bool sphere_roots(d3 o, d3 d, d3 c, double r, double tmin, double tmax, double& t) {
@@ -675,6 +679,8 @@ struct f3 {
 };
 __device__ __forceinline__ f3 mkf(float x, float y, float z) { return f3{x, y, z}; }
 
+// kShared: `tab` is a copy staged in shared memory (plain loads), else the table in global memory (read-only path)
+template <bool kShared = false>
 __device__ __forceinline__ float perlin_noise(const DPerlin* __restrict__ tab, float px, float py, float pz) {  // noise.rs:49-94
     float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     float u = px - fx, v = py - fy, w = pz - fz;
@@ -690,7 +696,8 @@ __device__ __forceinline__ float perlin_noise(const DPerlin* __restrict__ tab, f
 #pragma unroll
             for (int dk = 0; dk < 2; ++dk) {
                 uint32_t hz = tab->perm[2][(k + dk) & 255];
-                float4 g = __ldg(reinterpret_cast<const float4*>(tab->ranvec[hx ^ hy ^ hz]));
+                const float4* gp = reinterpret_cast<const float4*>(tab->ranvec[hx ^ hy ^ hz]);
+                float4 g = kShared ? *gp : __ldg(gp);
                 float wu = di ? uu : 1.f - uu, wv = dj ? vv : 1.f - vv, wwt = dk ? ww : 1.f - ww;
                 acc += wu * wv * wwt * (g.x * (u - di) + g.y * (v - dj) + g.z * (w - dk));
             }
@@ -698,11 +705,12 @@ __device__ __forceinline__ float perlin_noise(const DPerlin* __restrict__ tab, f
     }
     return acc;
 }
+template <bool kShared = false>
 __device__ __forceinline__ float perlin_turbulence(const DPerlin* tab, float px, float py, float pz) {  // noise.rs:96-108, depth 7
     float acc = 0.f, weight = 1.f;
 #pragma unroll 1
     for (int i = 0; i < 7; ++i) {
-        acc += weight * perlin_noise(tab, px, py, pz);
+        acc += weight * perlin_noise<kShared>(tab, px, py, pz);
         weight *= 0.5f;
         px *= 2.f; py *= 2.f; pz *= 2.f;
     }
@@ -725,15 +733,17 @@ __device__ __forceinline__ DTexture resolve_texture(const SceneView& sc, int32_t
     return t;
 }
 // NoiseTexture::value, texture.rs:52-59 (Q22): grey 0.5 (1 + sin(scale z + 10 turb(p)))
+template <bool kShared = false>
 __device__ __forceinline__ float noise_value(const SceneView& sc, int32_t perlin, float scale, float px, float py, float pz) {
-    float turb = perlin_turbulence(sc.perlins + perlin, px, py, pz);
+    float turb = perlin_turbulence<kShared>(sc.perlins + perlin, px, py, pz);
     return 0.5f * (1.f + sinf(scale * pz + 10.f * turb));
 }
 // Texture::value of a resolved texture. (u, v) are only meaningful when the texture's uses-uv flag is set.
+template <bool kShared = false>
 __device__ __forceinline__ f3 texture_eval(const SceneView& sc, const DTexture& t, float u, float v, d3 p) {
     if (t.kind == RTX_TEX_SOLID) return mkf(t.f[0], t.f[1], t.f[2]);
     if (t.kind == RTX_TEX_NOISE) {
-        float g = noise_value(sc, t.a, t.f[0], (float)p.x, (float)p.y, (float)p.z);
+        float g = noise_value<kShared>(sc, t.a, t.f[0], (float)p.x, (float)p.y, (float)p.z);
         return mkf(g, g, g);
     }
     if (t.kind == RTX_TEX_IMAGE) {  // texture.rs:77-106 (Q23): nearest texel, bytes / 255
@@ -790,7 +800,7 @@ __device__ __forceinline__ void apply_albedo(PathColor& pc, const Albedo& al) {
     }
 }
 
-template <bool kDeferNoise>
+template <bool kDeferNoise, bool kPerlinShared = false>
 __device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __restrict__ background, int32_t max_depth, RayD& ray,
                                           const Best& best, const Sampler& smp, PathColor& pc, int& bounce, Albedo& al) {
     bool end_path = false;
@@ -831,7 +841,7 @@ __device__ __forceinline__ bool shade_hit(const SceneView& sc, const float* __re
                 al.noise_scale = t.f[0];
                 al.px = (float)ho.p.x; al.py = (float)ho.p.y; al.pz = (float)ho.p.z;
             } else {
-                f3 tex = texture_eval(sc, t, tu, tv, ho.p);
+                f3 tex = texture_eval<kPerlinShared>(sc, t, tu, tv, ho.p);
                 alb_r = tex.x; alb_g = tex.y; alb_b = tex.z;
             }
         }

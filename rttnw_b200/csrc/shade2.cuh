@@ -4,19 +4,21 @@
 //
 //  * The sample dispenser. The first form read the dispenser ("already dry?") and then did the atomic, two dependent L2
 //    round trips at the very end of the warp's critical path (16.7 % of its stall samples, kernels.cuh:1245 and the
-//    atomicAdd). Here the read is issued with the first pool load, at the top of the kernel. (Leaving an ended slot empty
-//    for one trace pass, so that the atomic could also be issued at the top, was measured: 529 M samples/s against 600 M
-//    — launches are tail-bound, a sixth fewer rays per launch made them 5 % shorter, not 17 %.)
+//    atomicAdd). Here the read is issued with the first pool load, at the top of the kernel; the atomic still follows
+//    the shading, because which lanes ended is only known then. Worth 5 % on the Cornell box (712 -> 752 M samples/s,
+//    40 % of whose slots end per pass), 0.5 % on the final scene.
 //  * ConstantMedium::hit (hittable.rs:740-796) after the surface search instead of before it. The first form evaluated
 //    every medium for every new ray — an f64 quadratic, a square root and a logarithm for the fog that fills the final
 //    scene — so that the scatter distance could bound the traversal. But the free-flight distance -ln(u) / density is
 //    known from one fp32 logarithm, and once the surface hit is known a ray cannot scatter unless that distance fits
 //    into [t_min, t_surface]: for the final scene's fog (mean free path 10^4 against surface distances of 10^2..10^3)
-//    that skips the boundary test for ~90 % of the rays. The closest candidate wins either way, so the answer is
+//    that skips the boundary test for every ray that hit a surface nearby: the medium tests per ray fall from 1.35 to
+//    0.57 (what is left are the rays that hit nothing, for which the segment is unbounded, and the small medium), while
+//    the traversal, no longer cut short by a scatter point, visits 4.5 % more nodes. The closest candidate wins either way, so the answer is
 //    the reference's whatever the order (SURVEY.md hard parts); the filter only uses bounds that err on the side of
 //    running the exact test.
 //
-// Same Philox counters, same results as the first form (tests/test_gpu_parity.py runs the render tests under both).
+// Same Philox counters, same results as the first form (tests/test_gpu_parity.py::test_other_kernel_forms_trace_the_same_rays).
 #pragma once
 #include "kernels.cuh"
 
@@ -65,7 +67,9 @@ __device__ __forceinline__ void media_after(const SceneView& sc, const RayD& ray
     }
 }
 
-template <bool kCount>
+// kPerlinShared (RTX_PERLIN_SMEM=1, scenes with exactly one Perlin table): the 4.75 KB table — 256 gradients and the three
+// byte permutations (noise.rs:5-29) — is staged in shared memory by every CTA and NoiseTexture::value reads it there.
+template <bool kCount, bool kPerlinShared = false>
 __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)) wf_shade2_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out,
                                                                                                    Counters* counters) {
     const unsigned FULL = 0xffffffffu;
@@ -78,6 +82,15 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
 
     int bounce = valid ? a.pool.bounce[i] : -2;
     const bool dry = __ldcg(a.next_item) >= a.total_items;  // read now, needed after the shading: its latency is covered
+    if constexpr (kPerlinShared) {
+        __shared__ DPerlin s_perlin;
+        static_assert(sizeof(DPerlin) % 16 == 0, "DPerlin is copied in 16-byte words");
+        const uint4* src = reinterpret_cast<const uint4*>(a.sc.perlins);
+        uint4* dst = reinterpret_cast<uint4*>(&s_perlin);
+        for (int k = tid; k < (int)(sizeof(DPerlin) / 16); k += kShadeBlock) dst[k] = __ldg(src + k);
+        __syncthreads();
+        a.sc.perlins = &s_perlin;
+    }
 
     // ---- shade: media first (a scatter point in front of the surface hit replaces it), then one level of color() ----
     RayD ray{mk(0, 0, 0), mk(0, 0, 1), 0.0};
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
         smp.bounce = (uint32_t)bounce;
         if (a.sc.n_media > 0) media_after(a.sc, ray, 0.001, best, smp, stack, tally);
         Albedo al;
-        const bool ended = shade_hit<false>(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce, al);
+        const bool ended = shade_hit<false, kPerlinShared>(a.sc, a.cam.background, a.max_depth, ray, best, smp, pc, bounce, al);
         apply_albedo(pc, al);
         if (ended) {
             atomicAdd(accum + smp.pixel, make_float4(pc.rad_r, pc.rad_g, pc.rad_b, 1.0f));  // one path sample done

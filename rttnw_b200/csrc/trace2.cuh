@@ -1,28 +1,32 @@
 // trace2.cuh — K2b, second form: the closest surface hit of every ray in flight, with the world BVH and the
 // traversal stacks in SHARED memory and the warp as a persistent scheduling unit.
 //
-// Why (profiles/r1_wf_trace_kernel_details.txt + the raw counters of the same capture): the first form of this
-// kernel (wf_trace_kernel, kernels.cuh) is bound by the L1TEX data pipe, not by issue slots —
-// l1tex__data_pipe_lsu_wavefronts 64 % of peak while active, long_scoreboard the top stall — because a warp whose
-// lanes sit in different nodes pays one L1 wavefront PER LANE for each of the four LDG.128 of a node and for each
-// local-memory stack access (2.2-2.5 of 32 bytes used per sector). That is also why none of the round-1 schedules
-// that raised the lanes per instruction gained anything: the wavefront count per ray is the same under all of them.
-// Here the node array (85 KB for the book-2 final scene) is staged once per CTA into shared memory as four planes of
-// 16-byte chunks (chunk c of node i at plane c, index i: the bank group is i mod 8 for every chunk, so lanes in
-// different nodes spread over the banks without a swizzle), the stack is a per-thread column of a shared array
-// (entry k of thread t at [k][t]: conflict-free by construction) with its top kept in a register, so the pop that
-// follows a miss is off the critical path, and nothing on the node loop touches L1.
+// Why it was built (profiles/r1_wf_trace_kernel_details.txt + the raw counters of the same capture): in the first form of
+// this kernel (wf_trace_kernel, kernels.cuh) the L1TEX data pipe is the busiest unit (l1tex__data_pipe_lsu_wavefronts
+// 64 % of peak while active) and long_scoreboard the top stall — a warp whose lanes sit in different nodes pays one L1
+// wavefront PER LANE for each of the four LDG.128 of a node and for each local-memory stack access (2.2-2.5 of 32
+// bytes used per sector) — and only 8.5 of 32 lanes are active per instruction. Here the node array (85 KB for the
+// book-2 final scene, 106 KB with the padding that spreads it over the banks) is staged once per CTA into shared
+// memory, the stack is a per-thread column of a shared array (entry k of thread t at [k][t]: conflict-free by
+// construction) with its top in a register, so the pop that follows a miss is off the critical path, and nothing in the
+// node loop touches L1; and the warp is a persistent scheduling unit that runs a small state machine instead of a plain
+// while-while loop: every lane is at an inner node, at a leaf, or idle (ray finished / none yet), and each round the
+// warp runs ONE kind of work, chosen by vote with two thresholds — leaves are tested once `t_leaf` lanes wait at one
+// (or nobody has a node left), idle lanes are refilled from the CTA's share of the pool once `t_refill` of them wait (or
+// nothing else is left to do), otherwise every lane that has a node takes up to `burst` node steps. t_leaf = t_refill
+// = 33 is the plain while-while loop with whole-warp refills.
 //
-// With L1 out of the way the binding resource is issue slots at whatever lane utilisation the schedule reaches, so
-// the warp runs a small state machine instead of a plain while-while loop: every lane is in one of three states —
-// at an inner node, at a leaf, or idle (ray finished / none yet) — and each round the warp runs ONE kind of work,
-// chosen by vote with two thresholds: leaves are tested once `t_leaf` lanes wait at one (or nobody has a node left),
-// idle lanes are refilled from the CTA's share of the pool once `t_refill` of them wait (or nothing else is left to
-// do), otherwise every lane that has a node takes up to `burst` node steps. t_leaf = t_refill = 33 is the plain
-// while-while loop with whole-warp refills.
+// What it measured (scene 9, one B200; DESIGN.md §4 has the table): L1 data-pipe load fell from 64 % to 31 % and the
+// local-memory traffic is gone, but a warp still issues once every 9.3 cycles (9.4 before): the kernel is bound by the
+// latency of its dependent chain (fetch, 12 FMAs, min / max, compare, branch) at the 6-7 warps per scheduler its
+// registers allow, not by L1. The votes (16 / 8 / 8) cut its warp instructions by 21 % against whole-warp refills and
+// by 8 % against the first form; alone it is 12 % faster than the first form (16.0 against 18.3 ms of trace time per
+// 17 spp). In production it is 5 % SLOWER (570 against 600 M samples/s): one CTA of 896 threads x 72 registers holds the
+// whole register file of its SM, so the other partition's shade kernel cannot share the SM with it the way it does with
+// the first form's 128-thread CTAs, and that overlap is worth more than the trace kernel gained. Opt-in (RTX_TRACE=2).
 //
 // Replaces the recursion of BvhTree::hit (hittable.rs:355-368) over Bound::hit (bound.rs:13-32); same answers as
-// wf_trace_kernel (tests/test_gpu_parity.py runs every render test under both).
+// wf_trace_kernel (tests/test_gpu_parity.py::test_other_kernel_forms_trace_the_same_rays).
 #pragma once
 #include "kernels.cuh"
 
@@ -256,7 +260,9 @@ namespace rtx {
 // form shows its warps waiting for taken off the critical path: the stack is a shared-memory column with its top in a
 // register (the pop that follows a miss was 11.6 % of all stall samples as a local-memory load; local stack traffic
 // used 2.2-2.5 of the 32 bytes of each sector it moved), and a node is two 32-byte loads instead of four 16-byte ones
-// (one L1 wavefront per lane per load instruction: the L1 data pipe was the busiest unit at 64 %).
+// (one L1 wavefront per lane per load instruction: the L1 data pipe was the busiest unit at 64 %). Measured: 596 M
+// samples/s against 604 M for the first form on scene 9, 746 against 752 on scene 7 — neither the local-memory stack
+// nor the number of node loads is what the first form waits for. Opt-in (RTX_TRACE=4).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -15,8 +15,18 @@
 // shared memory) run side by side on different warps, so the two kinds of latency cover each other; two barriers
 // separate the rounds. The world BVH is staged in shared memory as in trace2.cuh.
 //
+// What it measured (scene 9, one B200): 25 of 32 lanes active per instruction, as designed — and 238-342 M
+// samples/s against 600 M. Moving a ray's 14 words of state in and out of shared memory, three list appends and the
+// round's bookkeeping cost ~260 thread instructions per ray and round, as much as four node steps, so the warp
+// instructions per ray only fell by 10 % (8.06 G against 8.94 G per 17 spp) while thread instructions tripled; and
+// rounds are as long as their slowest chunk (an f64 leaf chunk behind two dependent global loads), during which most
+// warps wait at the barrier: 0.72 instructions per cycle and SM against 2.3. Regrouping through shared memory pays
+// only if a round does much more than four steps per ray, and then the lanes diverge again inside the round. Kept as
+// a measured negative result, opt-in (RTX_TRACE=3).
+//
 // Replaces the recursion of BvhTree::hit (hittable.rs:355-368) over Bound::hit (bound.rs:13-32) and the List::hit
-// scan of the leaves (hittable.rs:153-163); same answers as the other forms (tests/test_gpu_parity.py).
+// scan of the leaves (hittable.rs:153-163); same answers as the other forms
+// (tests/test_gpu_parity.py::test_other_kernel_forms_trace_the_same_rays).
 #pragma once
 #include "trace2.cuh"
 

@@ -172,6 +172,7 @@ extern "C" {
     pub fn rtx_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut rtx_ctx) -> c_int;
     pub fn rtx_ctx_destroy(ctx: *mut rtx_ctx) -> c_int;
     pub fn rtx_ctx_sync(ctx: *mut rtx_ctx) -> c_int;
+    pub fn rtx_ctx_set_async(ctx: *mut rtx_ctx, on: c_int) -> c_int;
     pub fn rtx_ctx_stream(ctx: *mut rtx_ctx) -> *mut c_void;
     pub fn rtx_ctx_set_bvh_builder(ctx: *mut rtx_ctx, kind: c_int) -> c_int;
     pub fn rtx_ctx_kernel_launches(ctx: *mut rtx_ctx, out: *mut u64) -> c_int;
@@ -180,6 +181,7 @@ extern "C" {
     pub fn rtx_ctx_measure_l2_read(ctx: *mut rtx_ctx, bytes: u64, repeats: c_int, gbytes_per_s: *mut f64) -> c_int;
     pub fn rtx_scene_create(ctx: *mut rtx_ctx, desc: *const rtx_scene_desc, out: *mut *mut rtx_scene) -> c_int;
     pub fn rtx_scene_destroy(scene: *mut rtx_scene) -> c_int;
+    pub fn rtx_cache_trim(device: c_int) -> c_int;
     pub fn rtx_scene_info(scene: *const rtx_scene, n_bvh_nodes: *mut i32, n_records: *mut i32, n_xform_ops: *mut i32, device_bytes: *mut i64) -> c_int;
     pub fn rtx_trace_rays(ctx: *mut rtx_ctx, scene: *const rtx_scene, n: i64, rays: *const rtx_ray, hits: *mut rtx_hit) -> c_int;
     pub fn rtx_trace_rays_device(ctx: *mut rtx_ctx, scene: *const rtx_scene, n: i64, d_rays: *const rtx_ray, d_hits: *mut rtx_hit) -> c_int;

@@ -164,7 +164,7 @@ impl Gpu {
             let result = (|| {
                 check(ffi::rtx_malloc(self.ctx, bytes, &mut accum))?;
                 check(ffi::rtx_memset_zero(self.ctx, accum, bytes))?;
-                // rtx_render takes at most 2^26 samples per pixel per call: a frame is rendered in chunks of sample indices
+                // rtx_render takes at most 2^24 samples per pixel per call: a frame is rendered in chunks of sample indices
                 let mut begin = 0usize;
                 while begin < samples {
                     let count = (samples - begin).min(1 << 20);

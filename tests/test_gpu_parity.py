@@ -114,22 +114,32 @@ def test_empty_and_degenerate_inputs(ctx):
 # ---------------------------------------------------------------------------
 # fixed rays on the nine scenes of scenes.rs
 # ---------------------------------------------------------------------------
+# Largest share of rays the oracle may flag as grazing ties (a comparison of the reference within 1e-9 relative of
+# flipping, for a candidate at or before the final hit) per scene and ray generation: twice what 10^6 rays per scene
+# showed in round 2 (scene 7: 0 / 0.18 % / 1.46 %; scene 9: 0 / 1.48 % / 3.51 %; scene 1: < 0.003 %; the others: none —
+# profiles/r2_parity.json has the counts of every run), floored at 0.02 %. Scene 9's later generations travel INSIDE the
+# ground boxes and meet the exactly coplanar side faces adjacent boxes share (scenes.rs:244-253); scene 7's graze the
+# walls the two boxes stand on: genuine two-primitive ties.
+MAX_TIES = {7: (2e-4, 4e-3, 3e-2), 9: (2e-4, 3e-2, 7e-2)}
+
+
 @pytest.mark.parametrize("number", range(1, 10))
 def test_fixed_rays_builtin_scene(ctx, number, earth_rgba):
+    from tests._record import record
     n = 60000 if number in (1, 9) else 100000
     rng = np.random.default_rng(0xF17ED + number)
     gsc = R.DeviceScene(ctx, R.BuiltinDesc(number))
     osc = O.OracleScene.builtin(number, earth=earth_rgba)  # the oracle's OWN restatement of scenes.rs
     cam, _ = osc.camera()
+    limits = MAX_TIES.get(number, (2e-4, 2e-4, 2e-4))
     primary = RY.camera_rays(cam, n, rng)
-    got, ref, st1 = check_rays(gsc, osc, primary)
+    got, ref, st1 = check_rays(gsc, osc, primary, min_ok=1.0 - limits[0])
     secondary = RY.secondary_rays(ref, primary, rng)
-    _, ref2, st2 = check_rays(gsc, osc, secondary)
+    _, ref2, st2 = check_rays(gsc, osc, secondary, min_ok=1.0 - limits[1])
     tertiary = RY.secondary_rays(ref2, secondary, rng)
-    # scene 9: rays that travel INSIDE the ground boxes meet the exactly coplanar side faces adjacent
-    # boxes share (scenes.rs:244-253) — genuine two-primitive ties, a few percent of the tertiary set
-    _, _, st3 = check_rays(gsc, osc, tertiary, min_ok=0.95 if number == 9 else 0.98)
+    _, _, st3 = check_rays(gsc, osc, tertiary, min_ok=1.0 - limits[2])
     assert st1["hits"] > 0.3 * n
+    record("fixed_rays_three_generations", f"scene_{number}", {"primary": st1, "secondary": st2, "tertiary": st3, "max_tie_share_allowed": limits})
     print(f"scene {number}: {st1} {st2} {st3}")
 
 
@@ -201,11 +211,9 @@ def test_fixed_rays_random_scene_trees(ctx, seed):
 TEN_MILLION = {  # scene: (instanced-geometry id range whose p is Q14-displaced, or None)
     1: None, 2: None, 3: None, 4: None, 5: None, 6: None, 7: (6, 18), 8: (6, 20), 9: (2411, 3411),
 }
-# Largest share of rays the oracle may flag as grazing ties (a comparison of the reference within 1e-9 relative of
-# flipping, for a candidate at or before the final hit), per scene: twice what the 10^7-ray run of round 2 observed
-# (profiles/r2_parity.json), floored at 1e-4. Scene 9's secondary rays travel inside the ground boxes and meet the
-# exactly coplanar side faces adjacent boxes share (scenes.rs:244-253): genuine two-primitive ties.
-MAX_TIE_SHARE = {1: 1e-4, 2: 1e-4, 3: 1e-4, 4: 1e-4, 5: 1e-4, 6: 2e-3, 7: 4e-3, 8: 2e-3, 9: 3.5e-2}
+# Largest share of the 10^7 rays (half primary, half secondary) the oracle may flag as grazing ties, per scene: twice the
+# share 10^6 rays per scene showed (half of the secondary shares above), floored at 0.01 %.
+MAX_TIE_SHARE = {1: 1e-4, 2: 1e-4, 3: 1e-4, 4: 1e-4, 5: 1e-4, 6: 1e-4, 7: 2e-3, 8: 1e-4, 9: 1.5e-2}
 
 
 def trace_on_device(gsc, rays):
@@ -321,18 +329,22 @@ def test_same_counter_low_depth_render(ctx, number, earth_rgba):
         got = gpu_sum(gsc, w, h, spp, seed=3, max_depth=depth).cpu().numpy()[..., :3]
         ref, _ = osc.render_sum(w, h, spp, seed=3, max_depth=depth)
         close = np.isclose(got, ref, rtol=2e-3, atol=2e-3).all(axis=2)
+        from tests._record import record
+        record("same_counter_render", f"scene_{number}_depth_{depth}", {"width": w, "height": h, "spp": spp, "pixels_agreeing": float(close.mean())})
         assert close.mean() > 0.97, (number, depth, close.mean())
 
 
 RENDER_CASES = {  # scene: (width, height, spp)
     2: (64, 36, 2048), 3: (64, 36, 2048), 4: (64, 36, 2048), 1: (48, 27, 2048),
-    5: (48, 27, 16384), 7: (40, 40, 24576), 8: (32, 32, 24576), 9: (40, 40, 8192),
+    5: (48, 27, 16384), 6: (40, 40, 16384), 7: (40, 40, 24576), 8: (32, 32, 24576), 9: (40, 40, 12288),
 }
 
 
 @pytest.mark.parametrize("number", sorted(RENDER_CASES))
 def test_render_parity_psnr(ctx, number, earth_rgba):
-    """BASELINE.json: at equal high spp, PSNR >= 35 dB and mean per-channel error <= 1/255."""
+    """BASELINE.json: at equal high spp, PSNR >= 35 dB and mean per-channel error <= 1/255. The numbers go to
+    r2_parity.json."""
+    from tests._record import record
     w, h, spp = RENDER_CASES[number]
     gsc = R.DeviceScene(ctx, R.BuiltinDesc(number))
     osc = O.OracleScene.builtin(number, earth=earth_rgba)
@@ -342,9 +354,33 @@ def test_render_parity_psnr(ctx, number, earth_rgba):
     ref = osc.tonemap(ref_sum, spp)
     p = psnr(got, ref)
     err = np.abs(got[..., :3].astype(np.float64).mean(axis=(0, 1)) - ref[..., :3].astype(np.float64).mean(axis=(0, 1)))
+    record("render_psnr", f"scene_{number}", {"width": w, "height": h, "spp": spp, "psnr_db": p, "mean_abs_error_per_channel_8bit": err.tolist(),
+                                              "mean_abs_pixel_error_8bit": float(np.abs(got[..., :3].astype(float) - ref[..., :3].astype(float)).mean())})
     print(f"scene {number}: PSNR {p:.2f} dB, mean per-channel error {err} /255")
     assert p >= 35.0
     assert (err <= 1.0).all()
+
+
+def test_render_parity_at_the_reference_resolution(ctx):
+    """The Cornell box at the reference's own 600x600 (src/main.rs:137-149) against the oracle: the GPU frame's linear
+    sums are box-filtered 4x4 to the 150x150 grid the oracle can afford at the same total sample count per output pixel
+    (the same camera, so an oracle pixel integrates exactly the area of 16 GPU pixels), then both are tonemapped."""
+    from tests._record import record
+    gsc = R.DeviceScene(ctx, R.BuiltinDesc(7))
+    osc = O.OracleScene.builtin(7)
+    spp = 640
+    acc = gpu_sum(gsc, 600, 600, spp, seed=31).cpu().numpy()
+    assert (acc[..., 3] == spp).all()
+    small = acc[..., :3].astype(np.float64).reshape(150, 4, 150, 4, 3).sum(axis=(1, 3))
+    got = osc.tonemap(small, 16 * spp)
+    ref_sum, _ = osc.render_sum(150, 150, 16 * spp, seed=32)
+    ref = osc.tonemap(ref_sum, 16 * spp)
+    p = psnr(got, ref)
+    err = np.abs(got[..., :3].astype(np.float64).mean(axis=(0, 1)) - ref[..., :3].astype(np.float64).mean(axis=(0, 1)))
+    record("render_psnr", "scene_7_600x600_vs_oracle_150x150", {"gpu": "600x600 x %d spp, linear sums box-filtered 4x4" % spp,
+           "oracle": "150x150 x %d spp" % (16 * spp), "psnr_db": p, "mean_abs_error_per_channel_8bit": err.tolist()})
+    print(f"scene 7 at 600x600: PSNR {p:.2f} dB, mean per-channel error {err} /255")
+    assert p >= 35.0 and (err <= 1.0).all()
 
 
 def test_spp_chunking_and_sharding_invariance(ctx):
@@ -554,7 +590,7 @@ def test_bad_arguments_are_refused(ctx):
     acc = gsc.new_accum(8, 8)
     lib = ctx.lib
     for bad in (abi.RenderParams(0, 8, 0, 1, 50, 0, 1), abi.RenderParams(8, 8, -1, 1, 50, 0, 1), abi.RenderParams(8, 8, 0, -1, 50, 0, 1),
-                abi.RenderParams(8, 8, 0, 1, -1, 0, 1), abi.RenderParams(8, 8, 0, (1 << 26) + 1, 50, 0, 1)):
+                abi.RenderParams(8, 8, 0, 1, -1, 0, 1), abi.RenderParams(8, 8, 0, (1 << 24) + 1, 50, 0, 1)):
         assert lib.rtx_render(ctx.h, gsc.h, C.byref(bad), acc.data_ptr(), None) == -1
     assert lib.rtx_render(ctx.h, gsc.h, None, acc.data_ptr(), None) == -1
     assert lib.rtx_trace_rays(ctx.h, gsc.h, -1, None, None) == -1
@@ -634,9 +670,9 @@ def test_wide_bvh_traversal_finds_the_same_hits(number, monkeypatch):
 # ---------------------------------------------------------------------------
 # round 2: the other kernel forms, the spread-out combine, NCCL behind the ABI, one process per GPU
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("form", ["RTX_TRACE=2", "RTX_TRACE=2 RTX_T_REFILL=16 RTX_T_LEAF=8 RTX_T_BURST=8", "RTX_TRACE=3 RTX_T_BURST=4",
-                                  "RTX_TRACE=4", "RTX_SHADE=1"])
-@pytest.mark.parametrize("number", [7, 9])
+@pytest.mark.parametrize("form", ["RTX_TRACE=2", "RTX_TRACE=2 RTX_T_REFILL=33 RTX_T_LEAF=33 RTX_T_BURST=100000", "RTX_TRACE=3 RTX_T_BURST=4",
+                                  "RTX_TRACE=4", "RTX_SHADE=1", "RTX_PERLIN_SMEM=0"])
+@pytest.mark.parametrize("number", [3, 7, 9])
 def test_other_kernel_forms_trace_the_same_rays(form, number, monkeypatch, earth_rgba):
     """Every opt-in form of the trace kernel (shared-memory BVH + persistent voted warps, sorted through shared memory,
     shared stack + 32-byte loads) and the first form of the shade kernel: the same rays, the same samples in the same
@@ -724,3 +760,49 @@ def test_cli_one_process_per_gpu(tmp_path):
     one = np.asarray(Image.open(tmp_path / "one.png")).astype(int)
     two = np.asarray(Image.open(tmp_path / "two.png")).astype(int)
     assert np.abs(one - two).max() <= 1
+
+
+def test_asynchronous_render_returns_at_once_and_gives_the_same_frame():
+    """rtx_ctx_set_async: rtx_render hands the wavefront driver's loop to the context's own thread and returns
+    immediately; rtx_ctx_sync (and every other call on the context) waits for it. Same frame as the synchronous call."""
+    import ctypes as C
+    import time
+    import torch
+    c = R.Context(0)
+    try:
+        gsc = R.DeviceScene(c, R.BuiltinDesc(9))
+        w = h = 800
+        sync_acc = gsc.new_accum(w, h)
+        gsc.render_into(sync_acc, 0, 64, seed=3)  # also brings the pool to its size for this job
+        c.sync()
+        sync_acc.zero_()
+        gsc.render_into(sync_acc, 0, 16, seed=3)
+        c.sync()
+        t0 = time.perf_counter()
+        gsc.render_into(sync_acc, 16, 64, seed=3)
+        t_sync_call = time.perf_counter() - t0
+        c.sync()
+        abi.check(c.lib.rtx_ctx_set_async(c.h, 1))
+        async_acc = gsc.new_accum(w, h)
+        gsc.render_into(async_acc, 0, 16, seed=3)
+        c.sync()
+        t0 = time.perf_counter()
+        gsc.render_into(async_acc, 16, 64, seed=3)
+        t_async_call = time.perf_counter() - t0
+        c.sync()  # waits for the worker thread, then for the stream
+        t_async_total = time.perf_counter() - t0
+        from tests._record import record
+        record("async_render", "scene_9_800x800_64spp", {"sync_call_ms": 1e3 * t_sync_call, "async_call_ms": 1e3 * t_async_call,
+                                                         "async_call_plus_sync_ms": 1e3 * t_async_total})
+        assert t_async_call < 0.005 and t_async_call < 0.1 * t_sync_call, (t_async_call, t_sync_call)
+        assert t_async_total > 0.5 * t_sync_call
+        assert torch.allclose(sync_acc, async_acc, rtol=1e-4, atol=1e-3)
+        # an invalid request fails at once (argument checks run in the caller), a valid one after an error still works
+        bad = abi.RenderParams(0, 8, 0, 1, 50, 0, 1)
+        assert c.lib.rtx_render(c.h, gsc.h, C.byref(bad), async_acc.data_ptr(), None) == 0  # queued ...
+        assert c.lib.rtx_ctx_sync(c.h) == -1  # ... and reported by the call that joins
+        abi.check(c.lib.rtx_ctx_sync(c.h))
+        abi.check(c.lib.rtx_ctx_set_async(c.h, 0))
+        gsc.close()
+    finally:
+        c.close()

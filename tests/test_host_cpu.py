@@ -258,3 +258,80 @@ def test_bench_arms_print_the_same_config():
     assert set(bench.config(ns, d, w, h)) == {"workload", "scene", "width", "height", "spp_per_gpu_per_step", "max_depth", "sharding", "l2"}
     for number in range(1, 10):
         assert bench.scene_defaults(number) == R.scene_defaults(number)  # bench.py's copy of the scene table
+
+
+# ---------------------------------------------------------------------------
+# struct layouts: C header (gcc offsetof) == ctypes (abi.py) == Rust #[repr(C)] (ffi.rs), field by field
+# ---------------------------------------------------------------------------
+_STRUCTS = {"rtx_node": abi.Node, "rtx_material": abi.Material, "rtx_texture": abi.Texture, "rtx_perlin": abi.Perlin,
+            "rtx_image": abi.Image, "rtx_camera": abi.Camera, "rtx_scene_desc": abi.SceneDesc, "rtx_ray": abi.Ray,
+            "rtx_hit": abi.Hit, "rtx_render_params": abi.RenderParams, "rtx_trace_stats": abi.TraceStats,
+            "rtx_scene_defaults": abi.SceneDefaults}
+
+
+def _rust_layout(src, name):
+    """(size, {field: offset}) of a #[repr(C)] struct of ffi.rs under the C layout rules."""
+    body = re.search(r"pub struct %s \{(.*?)\n\}" % name, src, re.S).group(1)
+
+    def size_align(t):
+        t = t.strip()
+        m = re.fullmatch(r"\[(.+); (\d+)\]", t)
+        if m:
+            s, a = size_align(m.group(1))
+            return s * int(m.group(2)), a
+        if t.startswith("*const") or t.startswith("*mut"):
+            return 8, 8
+        if t.startswith("rtx_"):  # a nested struct (all of ours hold an 8-byte member)
+            return _rust_layout(src, t)[0], 8
+        return {"i32": (4, 4), "u32": (4, 4), "f32": (4, 4), "f64": (8, 8), "u64": (8, 8), "i64": (8, 8), "u8": (1, 1), "usize": (8, 8)}[t]
+    off, align, fields = 0, 1, {}
+    for fname, ftype in re.findall(r"pub (\w+): ([^,\n]+),", body):
+        s, a = size_align(ftype)
+        off = (off + a - 1) // a * a
+        fields[fname] = off
+        off += s
+        align = max(align, a)
+    return (off + align - 1) // align * align, fields
+
+
+def test_struct_layouts_header_ctypes_and_rust_agree(tmp_path):
+    ffi = open(os.path.join(ROOT, "rust", "rttnw-b200-sys", "src", "ffi.rs")).read()
+    # the header's own layout, from the C compiler
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rttnw_b200.h"', 'int main(void) {']
+    for cname, ct in _STRUCTS.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    c_layout = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in _STRUCTS.items():
+        rsize, rfields = _rust_layout(ffi, cname)
+        assert int(c_layout[cname]) == C.sizeof(ct) == rsize, (cname, c_layout[cname], C.sizeof(ct), rsize)
+        assert [f for f, _ in ct._fields_] == list(rfields), cname  # same fields in the same order
+        for fname, _ in ct._fields_:
+            assert int(c_layout[f"{cname}.{fname}"]) == getattr(ct, fname).offset == rfields[fname], (cname, fname)
+
+
+def test_rust_crate_describes_every_trait_object_of_the_reference():
+    """The host crate cannot be compiled here (no Rust toolchain): keep its surface in step with the reference's
+    re-exports (src/math/mod.rs:10-19) name by name — every Hittable / Material / Texture has a `describe`."""
+    math = open(os.path.join(ROOT, "rust", "rttnw-b200-sys", "src", "math.rs")).read()
+    hittables = ["Sphere", "MovingSphere", "List", "BvhTree", "Rectangle<M, P>", "Cube", "Translate", "YRotate", "ConstantMedium"]
+    materials = ["Lambertian<T>", "Metal", "Dielectric", "DiffuseLight", "Isotropic"]
+    textures = ["Vec3f<Color>", "CheckerTexture", "NoiseTexture", "ImageTexture"]
+    for trait, names in (("Hittable", hittables), ("Material", materials), ("Texture", textures)):
+        for n in names:
+            m = re.search(r"impl(<[^>]*>)? %s for %s \{\s*fn describe" % (trait, re.escape(n)), math)
+            assert m, f"math.rs: no `impl {trait} for {n}` with describe"
+    for name in ("XY", "XZ", "YZ", "Xy", "Xz", "Yz", "Plane", "Perlin", "CameraDescriptor", "Color", "Position", "Coordinate"):
+        assert re.search(r"\b%s\b" % name, math), name
+    scenes = open(os.path.join(ROOT, "rust", "rttnw-b200-sys", "src", "scenes.rs")).read()
+    assert 'include!(concat!(env!("RTTNW_REFERENCE_SRC"), "/scenes.rs"))' in scenes  # the reference's file, not a copy
+    render = open(os.path.join(ROOT, "rust", "rttnw-b200-sys", "src", "render.rs")).read()
+    assert "pub fn render(mut width: u32, mut aspect_ratio: f64, mut samples: usize, scene: usize) -> Option<()>" in render
+    for n in range(1, 10):
+        assert f'"{R.scene_defaults(n)["name"]}"' in render
