@@ -604,7 +604,8 @@ def run_ours(args):
             sc = R.DeviceScene(ctx, R.BuiltinDesc(number))
             fr = Frame(env, dd["width"], dd["height"], combine if combine != "local" else args.combine)
             fr.zero()
-            fr.render(sc.h, 0, 8, dd["max_depth"])  # warm-up (pool allocation for this size)
+            fr.render(sc.h, 0, 8, dd["max_depth"])  # warm-up: pool allocation for this size, and the first collective of
+            fr.combine_and_tonemap()                 # the frame's communicator (NCCL connects lazily: ~1 s)
             ctx.sync()
             frames[name] = one_frame(number, args.cornell_spp, fr, sc)
             sc.close()

@@ -8,19 +8,31 @@
 // next sample index it would render to PATH.<gpu>; --resume reloads them (same scene, size, spp, seed, gpus)
 // and carries on. Samples are keyed by their global index, so a resumed image equals an uninterrupted one up
 // to fp32 summation order.
-// With --gpus N the samples are sharded by global sample index, one PROCESS per device, each seeing ONLY its device
-// (CUDA_VISIBLE_DEVICES is narrowed before the process touches CUDA): on an 8-GPU box the CUDA runtime takes 6-7 s to
-// initialise when it can see every device, whether one context is created or eight, in one process or in eight
-// (profiles/r2_multi_gpu_8.txt) — that, not the render, was 7.5 s of round 1's 9 s. The parent forks ranks 1..N-1
-// before it touches CUDA and renders rank 0's share itself. Processes that cannot see each other's devices cannot map
-// each other's memory, so the end-of-frame combine goes through the host: every child copies its accumulator (10 MB at
-// 800x800) into a shared mapping and exits; the parent uploads them and runs the same fused sum + tonemap kernel on local
-// copies (a few milliseconds per frame). RTTNW_SINGLE_PROCESS=1 keeps one process with a thread per device and the
-// peer-mapped combine over NVLink; the NCCL combine (rtx_comm_*, rtx_accum_reduce) is what bench.py uses across ranks.
+// --gpus N. What costs time on a multi-GPU box is not the render but bringing CUDA up (measured on an 8 x B200 box,
+// profiles/r2_cli_wallclock.txt): 0.8 s per VISIBLE device in one process (6.6 s with all eight, whether one context
+// is created or eight), and processes that initialise at the same time queue behind each other (8 processes, each seeing
+// one device: the last one is up after 9.4 s) — against 1.3 s for the 10 000-spp final scene on eight GPUs. So:
+//   * every process sees ONLY its device (CUDA_VISIBLE_DEVICES is narrowed before its first CUDA call): one GPU is up
+//     in 0.9 s instead of 6.6 s;
+//   * the parent brings its own device up first, alone, THEN starts one worker process per further device (fork + exec
+//     of this binary with --worker) and begins to render at once; the workers bring CUDA up one after the other behind
+//     it, each waiting for the previous one (start-ups that overlap all finish together, after ~1.1 s x their number);
+//   * the samples are not divided in advance: every process claims chunks of global sample indices from a counter in
+//     a shared mapping until none are left, so a device that is up early renders more, and a device that is not up by
+//     the time the frame is finished is not waited for (the parent ends it). Samples are keyed by their global index, so
+//     the frame is the same whichever process rendered what (up to fp32 summation order);
+//   * processes that see one device each cannot map each other's memory, so the end-of-frame combine goes through the
+//     host: a worker copies its accumulator (10 MB at 800x800) into the shared mapping, the parent uploads the
+//     accumulators that hold samples and runs the fused sum + tonemap kernel on local copies (milliseconds per frame).
+// With --checkpoint / --resume (which need the sample ranges of a rank to be contiguous), or RTTNW_SINGLE_PROCESS=1,
+// one process drives the N devices with a thread each, static ranges and the peer-mapped combine over NVLink.
+#include <signal.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -81,23 +93,34 @@ static bool read_checkpoint(const std::string& path, CheckpointHeader& h, std::v
     return ok;
 }
 
-// Narrows CUDA_VISIBLE_DEVICES to the `rank`-th device this process could see (the rank-th entry of the variable when the
-// user set one, else device `rank`). Must run before the first CUDA call of the process; the device is then number 0.
-static void see_only_device(int rank) {
+// Narrows CUDA_VISIBLE_DEVICES to the `rank`-th device the user could see (`list`: the user's own CUDA_VISIBLE_DEVICES,
+// empty = all devices). Must run before the first CUDA call of the process; the device is then number 0.
+static void see_only_device(const std::string& list, int rank) {
     std::string pick = std::to_string(rank);
-    if (const char* cur = std::getenv("CUDA_VISIBLE_DEVICES")) {
-        std::string list = cur;
+    if (!list.empty()) {
         size_t pos = 0;
         for (int i = 0; i < rank && pos != std::string::npos; ++i) {
             pos = list.find(',', pos);
             if (pos != std::string::npos) ++pos;
         }
-        if (pos == std::string::npos || pos >= list.size()) return;  // fewer entries than ranks: leave it, rtx_ctx_create will say so
-        size_t end = list.find(',', pos);
-        pick = list.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+        if (pos == std::string::npos || pos >= list.size()) pick = "no-such-device";  // fewer entries than ranks: rtx_ctx_create will say so
+        else {
+            size_t end = list.find(',', pos);
+            pick = list.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+        }
     }
     setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
 }
+
+// What the processes of one multi-GPU render share (an anonymous memory file, inherited across exec).
+struct SharedFrame {
+    std::atomic<int> next_sample;  // first global sample index nobody has claimed yet
+    std::atomic<int> state[16];    // per rank: 0 not up yet, 1 claiming / rendering, 2 finished (accumulator in its slot, if it has samples)
+    std::atomic<int> samples[16];  // per rank: samples per pixel it rendered
+    int rc[16];
+    char pad[64];
+    // followed by (gpus - 1) accumulators of width * height float4, rank r in slot r - 1
+};
 
 int main(int argc, char** argv) {
     int scene = -1, spp = -1, width = -1, height = -1, gpus = 1, chunk = 256, ckpt_every = 1, stop_after = -1;
@@ -105,6 +128,8 @@ int main(int argc, char** argv) {
     unsigned long long seed = 1, scene_seed = 0;
     bool have_scene_seed = false;
     std::string out = "image.png";
+    int worker_rank = -1, shm_fd = -1;  // --worker R --shm-fd FD --device-list L: a worker process of a multi-GPU render (internal)
+    std::string device_list = std::getenv("CUDA_VISIBLE_DEVICES") ? std::getenv("CUDA_VISIBLE_DEVICES") : "";
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&](const char* name) -> const char* {
@@ -123,6 +148,9 @@ int main(int argc, char** argv) {
         else if (a == "--checkpoint-every") ckpt_every = std::atoi(next("--checkpoint-every"));
         else if (a == "--resume") resume_path = next("--resume");
         else if (a == "--stop-after-chunks") stop_after = std::atoi(next("--stop-after-chunks"));
+        else if (a == "--worker") worker_rank = std::atoi(next("--worker"));
+        else if (a == "--shm-fd") shm_fd = std::atoi(next("--shm-fd"));
+        else if (a == "--device-list") device_list = next("--device-list");
         else if (scene < 0 && !a.empty() && a[0] != '-') {
             char* end = nullptr;
             long v = std::strtol(a.c_str(), &end, 10);
@@ -131,14 +159,14 @@ int main(int argc, char** argv) {
         } else { usage(argv[0]); std::fprintf(stderr, "Error: There was an error\n"); return 1; }
     }
     if (scene < 0) { usage(argv[0]); std::fprintf(stderr, "Error: There was an error\n"); return 1; }
-    std::printf("Scene number: %d\n", scene);
+    if (worker_rank < 0) std::printf("Scene number: %d\n", scene);
     auto t0 = std::chrono::steady_clock::now();
     rtx_scene_defaults def;
     if (rtx_builtin_scene_defaults(scene, &def) != RTX_OK) {
         std::fprintf(stderr, "%s\nError: There was an error\n", rtx_last_error());  // main.rs:179-182
         return 1;
     }
-    std::printf("Running scene %s\n", def.name);
+    if (worker_rank < 0) std::printf("Running scene %s\n", def.name);
     if (spp < 0) spp = def.samples;
     if (width < 0) width = def.width;
     if (height < 0) height = def.height;
@@ -153,7 +181,8 @@ int main(int argc, char** argv) {
         if (verbose) std::fprintf(stderr, "[%8.3f s] %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
     };
     lap("scene description built");
-    const bool one_device_per_process = std::getenv("RTTNW_SINGLE_PROCESS") == nullptr;
+    const bool static_ranges = !ckpt_path.empty() || !resume_path.empty() || stop_after >= 0;
+    const bool one_device_per_process = std::getenv("RTTNW_SINGLE_PROCESS") == nullptr && !(gpus > 1 && static_ranges);
     std::vector<Rank> ranks((size_t)gpus);
     auto worker = [&](int r) {
         Rank& k = ranks[(size_t)r];
@@ -210,78 +239,147 @@ int main(int argc, char** argv) {
     };
     const bool multi_process = gpus > 1 && one_device_per_process;
     std::vector<const float*> peers;
-    if (!multi_process && one_device_per_process) see_only_device(0);
-    if (multi_process) {
+    if (!multi_process && one_device_per_process && worker_rank < 0) see_only_device(device_list, 0);
+    if (multi_process || worker_rank >= 0) {
+        if (gpus > 16) { std::fprintf(stderr, "at most 16 GPUs\n"); return 1; }
         const size_t frame_bytes = (size_t)width * height * 4 * sizeof(float);
-        // one slot per child for its accumulator, shared with the parent; a pipe per child for its status
-        float* shared = (float*)mmap(nullptr, frame_bytes * (size_t)(gpus - 1), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
-        if (shared == MAP_FAILED) { std::perror("mmap"); return 1; }
-        struct Child {
-            pid_t pid = -1;
-            int up = -1;
+        const size_t shm_bytes = sizeof(SharedFrame) + frame_bytes * (size_t)(gpus - 1);
+        const int me = worker_rank >= 0 ? worker_rank : 0;
+        if (me == 0) {
+            shm_fd = memfd_create("rttnw-frame", 0);  // (no MFD_CLOEXEC: the workers inherit it across exec)
+            if (shm_fd < 0 || ftruncate(shm_fd, (off_t)shm_bytes) != 0) { std::perror("memfd_create"); return 1; }
+        }
+        void* map = mmap(nullptr, shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, shm_fd, 0);
+        if (map == MAP_FAILED) { std::perror("mmap"); return 1; }
+        SharedFrame* sh = (SharedFrame*)map;  // (a fresh memory file is zero-filled: every counter starts at 0)
+        float* slots = (float*)((char*)map + sizeof(SharedFrame));
+        see_only_device(device_list, me);
+        Rank& k = ranks[(size_t)me];
+        auto chk = [&](int rc) { if (rc != RTX_OK && k.rc == 0) { k.rc = rc; std::fprintf(stderr, "gpu %d: %s\n", me, rtx_last_error()); } return rc == RTX_OK; };
+        auto bring_up = [&]() {
+            if (!chk(rtx_ctx_create(0, nullptr, &k.ctx))) return;
+            if (me == 0) lap("context created");
+            if (!chk(rtx_scene_create(k.ctx, desc, &k.scene))) return;
+            if (!chk(rtx_malloc(k.ctx, frame_bytes, (void**)&k.accum))) return;
+            if (!chk(rtx_memset_zero(k.ctx, k.accum, frame_bytes))) return;
         };
-        std::vector<Child> children;
+        // claim chunks of global sample indices until none are left (chunks small enough that the devices finish together)
+        const int dyn_chunk = std::max(16, std::min(chunk, spp / (gpus * 6)));
+        auto claim_loop = [&]() {
+            sh->state[me].store(1);  // from here on the parent waits for this rank
+            int mine = 0;
+            for (;;) {
+                const int b0 = sh->next_sample.fetch_add(dyn_chunk);
+                if (b0 >= spp) break;
+                rtx_render_params p;
+                std::memset(&p, 0, sizeof(p));
+                p.width = width; p.height = height; p.spp_begin = b0; p.spp_count = (spp - b0 < dyn_chunk) ? spp - b0 : dyn_chunk;
+                p.max_depth = def.max_depth; p.seed = seed;
+                if (!chk(rtx_render(k.ctx, k.scene, &p, k.accum, nullptr))) return;
+                mine += p.spp_count;
+            }
+            chk(rtx_ctx_sync(k.ctx));
+            sh->samples[me].store(mine);
+        };
+        if (me != 0) {  // ---- a worker: render what it can claim, leave the accumulator in its slot, end ----
+            // CUDA start-ups that overlap slow each other down so that all finish together after ~1.1 s x their number;
+            // one after the other each takes ~0.9 s and its device starts rendering right away: wait for the previous
+            // rank to be up (or for the frame to be fully claimed, in which case this device is not needed at all)
+            while (sh->state[me - 1].load() == 0 && sh->next_sample.load() < spp) usleep(300);
+            if (sh->next_sample.load() >= spp) {
+                sh->rc[me] = 0;
+                sh->state[me].store(2);
+                _exit(0);
+            }
+            bring_up();
+            if (k.rc == 0) claim_loop();
+            if (k.rc == 0 && sh->samples[me].load() > 0 &&
+                rtx_memcpy_d2h(k.ctx, (char*)slots + frame_bytes * (size_t)(me - 1), k.accum, frame_bytes) != RTX_OK) {
+                std::fprintf(stderr, "gpu %d: %s\n", me, rtx_last_error());
+                k.rc = 1;
+            }
+            sh->rc[me] = k.rc;
+            sh->state[me].store(2);
+            _exit(k.rc == 0 ? 0 : 1);  // (no teardown: the process ends here and the driver reclaims the device)
+        }
+        // ---- the parent: its own device first and alone, then the workers behind it ----
+        bring_up();
+        if (k.rc != 0) return 1;
+        lap("scene uploaded");
+        std::vector<pid_t> pids((size_t)gpus, -1);
         std::fflush(stdout);
         std::fflush(stderr);
         for (int r = 1; r < gpus; ++r) {
-            int up[2];
-            if (pipe(up) != 0) { std::perror("pipe"); return 1; }
             pid_t pid = fork();
-            if (pid < 0) { std::perror("fork"); return 1; }
-            if (pid == 0) {  // rank r: sees its device only, renders its share, leaves the accumulator in the shared mapping
-                close(up[0]);
-                see_only_device(r);
-                worker(r);
-                Rank& k = ranks[(size_t)r];
-                int32_t rc = k.rc;
-                if (rc == 0 && rtx_memcpy_d2h(k.ctx, (char*)shared + frame_bytes * (size_t)(r - 1), k.accum, frame_bytes) != RTX_OK) {
-                    std::fprintf(stderr, "gpu %d: %s\n", r, rtx_last_error());
-                    rc = 1;
-                }
-                ssize_t w = write(up[1], &rc, sizeof(rc));
-                (void)w;
-                _exit(rc == 0 ? 0 : (rc == 3 ? 3 : 1));  // (no teardown: the process ends here and the driver reclaims the device)
+            if (pid < 0) { std::perror("fork"); break; }
+            if (pid == 0) {
+                std::vector<std::string> args(argv, argv + argc);
+                for (const char* extra : {"--worker", "", "--shm-fd", "", "--device-list", ""}) args.push_back(extra);
+                args[args.size() - 5] = std::to_string(r);
+                args[args.size() - 3] = std::to_string(shm_fd);
+                args[args.size() - 1] = device_list;
+                std::vector<char*> cargs;
+                for (auto& a : args) cargs.push_back(const_cast<char*>(a.c_str()));
+                cargs.push_back(nullptr);
+                execv("/proc/self/exe", cargs.data());
+                std::perror("execv");
+                _exit(127);
             }
-            close(up[1]);
-            Child c;
-            c.pid = pid; c.up = up[0];
-            children.push_back(c);
+            pids[(size_t)r] = pid;
         }
-        see_only_device(0);
-        worker(0);
-        int bad = ranks[0].rc;
-        for (size_t i = 0; i < children.size(); ++i) {
-            int32_t rc = 1;
-            if (read(children[i].up, &rc, sizeof(rc)) != (ssize_t)sizeof(rc)) { rc = 1; std::fprintf(stderr, "gpu %zu: worker process died\n", i + 1); }
-            close(children[i].up);
-            if (rc != 0 && bad == 0) bad = rc;
+        claim_loop();
+        if (k.rc != 0) { for (int r = 1; r < gpus; ++r) if (pids[(size_t)r] > 0) { kill(pids[(size_t)r], SIGKILL); waitpid(pids[(size_t)r], nullptr, 0); } return 1; }
+        lap("render finished");
+        // every sample index is claimed now. A worker that has not begun to claim can get nothing any more: end it, do
+        // not wait for its CUDA start-up; wait for the ones that hold samples.
+        int bad = 0, used = 1;
+        for (int r = 1; r < gpus; ++r) {
+            if (pids[(size_t)r] <= 0) continue;
+            if (sh->state[r].load() == 0) {
+                kill(pids[(size_t)r], SIGKILL);
+            } else {
+                while (sh->state[r].load() != 2) {
+                    int st = 0;
+                    if (waitpid(pids[(size_t)r], &st, WNOHANG) == pids[(size_t)r]) {  // died without reporting
+                        if (sh->state[r].load() != 2) { std::fprintf(stderr, "gpu %d: worker process died\n", r); bad = 1; }
+                        pids[(size_t)r] = -1;
+                        break;
+                    }
+                    usleep(200);
+                }
+                if (sh->state[r].load() == 2 && sh->rc[r] != 0) bad = 1;
+                if (sh->samples[r].load() > 0) ++used;
+            }
         }
-        if (bad != 0) {
-            for (auto& c : children) { int st = 0; waitpid(c.pid, &st, 0); }
-            return bad == 3 ? 3 : 1;
+        if (verbose) {
+            std::fprintf(stderr, "           samples per pixel by rank:");
+            for (int r = 0; r < gpus; ++r) std::fprintf(stderr, " %d", sh->samples[r].load());
+            std::fprintf(stderr, "  (%d of %d devices were up in time)\n", used, gpus);
         }
+        if (bad != 0) { for (int r = 1; r < gpus; ++r) if (pids[(size_t)r] > 0) waitpid(pids[(size_t)r], nullptr, 0); return 1; }
         lap("all ranks finished");
         std::vector<void*> staged;
         for (int r = 1; r < gpus; ++r) {
+            if (sh->samples[r].load() <= 0) continue;
             void* d = nullptr;
-            RTX(rtx_malloc(ranks[0].ctx, frame_bytes, &d));
-            RTX(rtx_memcpy_h2d(ranks[0].ctx, d, (char*)shared + frame_bytes * (size_t)(r - 1), frame_bytes));
+            RTX(rtx_malloc(k.ctx, frame_bytes, &d));
+            RTX(rtx_memcpy_h2d(k.ctx, d, (char*)slots + frame_bytes * (size_t)(r - 1), frame_bytes));
             staged.push_back(d);
             peers.push_back((const float*)d);
         }
         std::vector<uint8_t> rgba_mp((size_t)width * height * 4);
         uint8_t* d_rgba_mp = nullptr;
-        RTX(rtx_malloc(ranks[0].ctx, rgba_mp.size(), (void**)&d_rgba_mp));
-        RTX(rtx_reduce_tonemap_peers(ranks[0].ctx, ranks[0].accum, peers.data(), (int)peers.size(), width, height, d_rgba_mp));
-        RTX(rtx_memcpy_d2h(ranks[0].ctx, rgba_mp.data(), d_rgba_mp, rgba_mp.size()));
+        RTX(rtx_malloc(k.ctx, rgba_mp.size(), (void**)&d_rgba_mp));
+        RTX(rtx_reduce_tonemap_peers(k.ctx, k.accum, peers.empty() ? nullptr : peers.data(), (int)peers.size(), width, height, d_rgba_mp));
+        RTX(rtx_memcpy_d2h(k.ctx, rgba_mp.data(), d_rgba_mp, rgba_mp.size()));
         lap("frame on the host");
         RTX(rtx_png_write_rgba8(out.c_str(), width, height, rgba_mp.data()));
         lap("png written");
         double secs_mp = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::printf("%.6fs\n", secs_mp);  // println!("{:?}", instant.elapsed())
         std::fflush(stdout);
-        for (auto& c : children) { int st = 0; waitpid(c.pid, &st, 0); }
-        _exit(0);  // like the children: no context teardown at the end of the process
+        for (int r = 1; r < gpus; ++r) if (pids[(size_t)r] > 0) waitpid(pids[(size_t)r], nullptr, 0);
+        _exit(0);  // like the workers: no context teardown at the end of the process
     }
     std::vector<std::thread> th;
     for (int r = 0; r < gpus; ++r) th.emplace_back(worker, r);
