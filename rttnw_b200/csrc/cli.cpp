@@ -337,6 +337,7 @@ int main(int argc, char** argv) {
             if (pids[(size_t)r] <= 0) continue;
             if (sh->state[r].load() == 0) {
                 kill(pids[(size_t)r], SIGKILL);
+                pids[(size_t)r] = -1;  // (not waited for: a process inside the CUDA start-up takes over a second to go; init reaps it)
             } else {
                 while (sh->state[r].load() != 2) {
                     int st = 0;

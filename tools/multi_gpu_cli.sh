@@ -29,6 +29,7 @@ a = png_read_rgba8('gpurun_out/cli_final_1.png').astype(int); b = png_read_rgba8
 print('1-GPU frame vs $N-GPU frame: max |difference|', np.abs(a - b).max(), 'mean', np.abs(a - b).mean())
 PY
 rm -f gpurun_out/cli_final_*.png gpurun_out/cli_cornell_[124].png
+[ -n "$SKIP_BENCH" ] && exit 0
 python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29573 --nproc-per-node $N bench.py --gpus $N --steps 4 > gpurun_out/cli_bench_$N.json 2> gpurun_out/cli_bench_$N.err
 python -c "
 import json; d=json.load(open('gpurun_out/cli_bench_$N.json')); print('bench', d['n_gpus'], d['value']/1e6, d['e2e']['value']/1e6, d['details']['combine'], {k:(round(v['seconds'],3)) for k,v in d['frames'].items()})"
