@@ -96,6 +96,11 @@ struct rtx_ctx {
     int trace_form = 1;
     int trace_threads = 896;               // CTA size of the shared-memory form, one CTA per SM (RTX_TRACE_THREADS: 896, 640, 512, 448)
     int t_leaf = 8, t_refill = 16, t_burst = 8;  // its vote thresholds (RTX_T_LEAF / RTX_T_REFILL / RTX_T_BURST); 33 / 33 / huge = plain while-while
+    // RTX_ORDER=1: the trace pass takes its rays in (direction octant, record they start on) order: order.cuh
+    int order_form = 0;
+    int order_groups = 512;                // record groups per octant (RTX_ORDER_GROUPS, a power of two)
+    void* d_order = nullptr;
+    size_t order_bytes = 0;
     int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int prof_stride = 8;                   // RTX_PROF_STRIDE: every n-th iteration of partition 0 is bracketed when profiling is on
     bool perlin_smem = true;               // the shade kernel stages the Perlin table (noise.rs:5-29) in shared memory when the scene has exactly one
@@ -107,7 +112,9 @@ struct rtx_ctx {
     cudaEvent_t fork_event = nullptr;
     unsigned long long wf_iterations = 0;  // (shade, trace) iterations launched on partition 0
     unsigned long long launches = 0;  // kernels launched by this context (rtx_ctx_kernel_launches)
-    int bvh_builder = 0;              // 0: host binned SAH (default), 1: device LBVH (rtx_ctx_set_bvh_builder, RTX_BVH=lbvh)
+    int bvh_builder = 0;              // 0: host binned SAH (default), 1: device LBVH, 2: device PLOC (rtx_ctx_set_bvh_builder, RTX_BVH=lbvh|ploc)
+    int ploc_radius = 16;             // neighbours searched on each side by the PLOC builder (RTX_PLOC_RADIUS, 1..32)
+    int last_build_passes = 0;        // passes the last PLOC build took (RTX_DEBUG_BUILD=1 prints it)
     uint8_t* h_stage = nullptr;       // pinned staging buffer of rtx_scene_create (every H2D copy leaves from here)
     size_t stage_bytes = 0;
     // optional per-kernel timing of the wavefront driver (rtx_ctx_set_profiling): CUDA events around every launch
@@ -240,9 +247,13 @@ int rtx_ctx_create(int device, void* stream, rtx_ctx** out) {
     c->debug_batches = env_int("RTX_DEBUG_BATCHES", 0) != 0;
     if (const char* v = std::getenv("RTX_PERLIN_SMEM")) c->perlin_smem = std::atoi(v) != 0;
     c->prof_stride = env_int("RTX_PROF_STRIDE", c->prof_stride);
+    if (const char* v = std::getenv("RTX_ORDER")) c->order_form = std::atoi(v);
+    c->order_groups = env_int("RTX_ORDER_GROUPS", c->order_groups);
+    { int g = 8; while (g * 2 <= c->order_groups && g < (1 << 15)) g *= 2; c->order_groups = g; }
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (const char* m = std::getenv("RTX_MODE")) c->mode = std::strcmp(m, "mega") == 0 ? 0 : 1;
-    if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : 0;
+    if (const char* m = std::getenv("RTX_BVH")) c->bvh_builder = std::strcmp(m, "lbvh") == 0 ? 1 : (std::strcmp(m, "ploc") == 0 ? 2 : 0);
+    c->ploc_radius = env_int("RTX_PLOC_RADIUS", c->ploc_radius);
     // the traversal stack lives in local memory: prefer L1 over shared for it
     cudaFuncSetCacheConfig(rtx::render_kernel<false>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(rtx::trace_rays_kernel<false>, cudaFuncCachePreferL1);
@@ -263,6 +274,7 @@ int rtx_ctx_destroy(rtx_ctx* c) {
     cudaFree(c->d_work_counter);
     cudaFree(c->d_counters);
     cudaFree(c->d_pool);
+    cudaFree(c->d_order);
     cudaFree(c->d_next_item);
     cudaFree(c->d_active);
     if (c->h_status) cudaFreeHost(c->h_status);
@@ -350,7 +362,7 @@ int rtx_ctx_measure_l2_read(rtx_ctx* c, unsigned long long bytes, int repeats, d
     return RTX_OK;
 }
 int rtx_ctx_set_bvh_builder(rtx_ctx* c, int kind) {
-    if (!c || kind < 0 || kind > 1) return fail(RTX_ERR_INVALID, "bad argument");
+    if (!c || kind < 0 || kind > 2) return fail(RTX_ERR_INVALID, "bad argument");
     c->bvh_builder = kind;
     return RTX_OK;
 }
@@ -368,7 +380,7 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
     CU(cudaSetDevice(c->device));
     rtx::FlatScene fs;
     std::string err;
-    if (!rtx::flatten_scene(*desc, fs, err, c->bvh_builder == 1, c->wf_wide != 0)) return fail(RTX_ERR_INVALID, "scene description: " + err);
+    if (!rtx::flatten_scene(*desc, fs, err, c->bvh_builder >= 1, c->wf_wide != 0)) return fail(RTX_ERR_INVALID, "scene description: " + err);
     // nodes the device builder will add behind the host-built ones (medium boundaries), and its box upload
     const size_t host_nodes = fs.nodes.size();
     const size_t lbvh_nodes = fs.world_deferred ? (size_t)fs.world_count - 1 : 0;
@@ -511,10 +523,20 @@ int rtx_scene_create(rtx_ctx* c, const rtx_scene_desc* desc, rtx_scene** out) {
             }
         for (int a = 0; a < 3; ++a) ext[a] -= lo[a];
         int depth = 0;
-        e = rtx::lbvh_build(c->stream, fs.world_count, (const float*)(base + off_boxes), lo, ext, fs.world_first_record, (int32_t)host_nodes,
-                            (rtx::BvhNode*)(base + off_nodes) + host_nodes, &depth);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "lbvh_build"));
-        c->launches += 4;
+        if (c->bvh_builder == 2) {
+            int passes = 0;
+            e = rtx::ploc_build(c->stream, fs.world_count, (const float*)(base + off_boxes), lo, ext, fs.world_first_record, (int32_t)host_nodes,
+                                (rtx::BvhNode*)(base + off_nodes) + host_nodes, &depth, c->ploc_radius, &passes);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "ploc_build"));
+            c->last_build_passes = passes;
+            c->launches += 4ull + 4ull * (unsigned long long)passes;
+            if (std::getenv("RTX_DEBUG_BUILD")) std::fprintf(stderr, "[rtx] PLOC: %d primitives, radius %d, %d passes, depth %d\n", fs.world_count, c->ploc_radius, passes, depth);
+        } else {
+            e = rtx::lbvh_build(c->stream, fs.world_count, (const float*)(base + off_boxes), lo, ext, fs.world_first_record, (int32_t)host_nodes,
+                                (rtx::BvhNode*)(base + off_nodes) + host_nodes, &depth);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "lbvh_build"));
+            c->launches += 4;
+        }
         if (1 + depth + 1 > rtx::kTraversalStack)
             return bail(fail(RTX_ERR_UNSUPPORTED, "device-built BVH deeper than the traversal stack: use the host builder"));
         fs.world_root = (int32_t)host_nodes;
@@ -659,11 +681,25 @@ int rtx_trace_rays_stats(rtx_ctx* c, const rtx_scene* s, int64_t n, const rtx_ra
 }
 
 // ---- render: wavefront driver ---------------------------------------------------
+static size_t order_bins_padded(int groups) {
+    const size_t unit = 4 * (size_t)rtx::kShadeBlock;
+    return ((size_t)8 * (size_t)groups + 1 + unit - 1) / unit * unit;
+}
 static int wf_prepare(rtx_ctx* c, int64_t slots) {
     if (slots > c->pool_slots) {
         if (c->d_pool) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->d_pool)); c->d_pool = nullptr; c->pool_slots = 0; }
         CU(cudaMalloc(&c->d_pool, (size_t)slots * rtx::kPoolBytesPerSlot + 256));
         c->pool_slots = (int)slots;
+    }
+    if (c->order_form != 0) {
+        // per partition: hist [bins], offsets [bins + 1], done, then per slot key_rank (8 B) and order (4 B)
+        const size_t bins = order_bins_padded(c->order_groups);
+        const size_t need = (size_t)c->wf_streams * ((2 * bins + 64) * 4) + (size_t)slots * 12 + 4096;
+        if (need > c->order_bytes) {
+            if (c->d_order) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->d_order)); c->d_order = nullptr; c->order_bytes = 0; }
+            CU(cudaMalloc(&c->d_order, need));
+            c->order_bytes = need;
+        }
     }
     if (!c->d_next_item) CU(cudaMalloc(&c->d_next_item, sizeof(unsigned long long)));
     if (!c->d_active) CU(cudaMalloc(&c->d_active, 8 * sizeof(unsigned int)));
@@ -736,6 +772,8 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     // streams the pool) can share the SMs with the trace kernel of another (issue bound). Partition 0 runs on the
     // ctx stream; the others fork from it here and join it at the end.
     const int P = (slots >= (int64_t)c->wf_streams * 4 * rtx::kWfBlock) ? c->wf_streams : 1;
+    const bool ordered = c->order_form != 0 && c->shade_form >= 2 && c->trace_form == 1 && !wide;
+    if (ordered) CU(cudaMemsetAsync(c->d_order, 0, (size_t)P * (2 * order_bins_padded(c->order_groups) + 64) * 4, c->stream));
     struct Part {
         rtx::WfArgs a;
         cudaStream_t stream;
@@ -756,6 +794,21 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             pt.a.pool.pixel += begin; pt.a.pool.sample += begin;
             float** f4[6] = {&pt.a.pool.thr_r, &pt.a.pool.thr_g, &pt.a.pool.thr_b, &pt.a.pool.rad_r, &pt.a.pool.rad_g, &pt.a.pool.rad_b};
             for (auto pp : f4) *pp += begin;
+            if (ordered) {
+                const size_t bins = order_bins_padded(c->order_groups);
+                uint32_t* w = (uint32_t*)c->d_order + (size_t)q * (2 * bins + 64);
+                rtx::OrderArgs& o = pt.a.order;
+                o.hist = w;
+                o.offsets = w + bins;
+                o.done = w + 2 * bins + 1;
+                uint8_t* per_slot = (uint8_t*)c->d_order + (((size_t)P * (2 * bins + 64) * 4 + 255) & ~(size_t)255);
+                o.key_rank = (uint2*)per_slot + begin;
+                o.order = (uint32_t*)(per_slot + (size_t)slots * 8) + begin;
+                o.n_bins_padded = (int32_t)bins;
+                o.groups = c->order_groups;
+                o.shift = 0;
+                while (((s->n_records - 1) >> o.shift) >= o.groups) ++o.shift;
+            }
             pt.grid = (unsigned)(count / rtx::kTraceBlock);
             pt.sgrid = (unsigned)(count / rtx::kShadeBlock);
             pt.done = false;
@@ -891,7 +944,13 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 prof_now = q == 0 && c->profiling && (iteration++ % kProfStride) == 0;
                 CU(prof_mark());
                 if (c->shade_form >= 2) {
-                    if (counted) rtx::wf_shade2_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                    if (counted && !ordered) rtx::wf_shade2_kernel<true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                    else if (ordered) {
+                        if (counted) rtx::wf_shade2_kernel<true, false, true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, c->d_counters);
+                        else if (c->perlin_smem && s->n_perlins == 1) rtx::wf_shade2_kernel<false, true, true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
+                        else rtx::wf_shade2_kernel<false, false, true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
+                        rtx::wf_order_kernel<<<(unsigned)((pt.a.n_slots + 255) / 256), 256, 0, pt.stream>>>(pt.a.order, pt.a.n_slots);
+                    }
                     else if (c->perlin_smem && s->n_perlins == 1) rtx::wf_shade2_kernel<false, true><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
                     else rtx::wf_shade2_kernel<false><<<pt.sgrid, rtx::kShadeBlock, 0, pt.stream>>>(pt.a, acc, active, nullptr);
                 } else {
@@ -900,7 +959,10 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 }
                 CU(prof_mark());
                 CU(prof_mark());
-                if (t1c) {
+                if (ordered) {
+                    if (counted) rtx::wf_trace_ordered_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.order, d_ray_count, c->d_counters);
+                    else rtx::wf_trace_ordered_kernel<false><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.order, d_ray_count, nullptr);
+                } else if (t1c) {
                     if (counted) rtx::wf_trace1c_kernel<true><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, c->d_counters);
                     else rtx::wf_trace1c_kernel<false><<<pt.grid, rtx::kTraceBlock, 0, pt.stream>>>(pt.a.sc, pt.a.pool, pt.a.n_slots, d_ray_count, nullptr);
                 } else if (t3_threads != 0) {
@@ -921,7 +983,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
                 CU(prof_mark());
             }
             CU(cudaGetLastError());
-            c->launches += 2ull * (unsigned long long)batch;
+            c->launches += (ordered ? 3ull : 2ull) * (unsigned long long)batch;
             if (q == 0) c->wf_iterations += (unsigned long long)batch;
             // status of this batch -> pinned memory (active is 32-bit: widen on the host side)
             unsigned long long* hs = c->h_status + 4 * q + 2 * par;

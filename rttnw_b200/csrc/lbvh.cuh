@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "device_types.h"
 
@@ -199,6 +200,187 @@ inline cudaError_t lbvh_build(cudaStream_t stream, int n, const float* d_boxes, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(block);
     if (depth_out) *depth_out = depth;
+    return e;
+}
+
+
+// ---------------------------------------------------------------------------
+// PLOC — parallel locally-ordered clustering (Meister & Bittner, "Parallel Locally-Ordered Clustering for Bounding
+// Volume Hierarchy Construction", TVCG 2018), the builder for scenes too large for the host and too incoherent for
+// an LBVH. Bottom-up agglomeration along the Morton curve: the clusters (at first the leaves, in Morton order) each
+// look r positions to the left and right for the neighbour whose union with them has the smallest surface area;
+// pairs that chose each other merge into an inner node that takes the place of the left partner; the array is
+// compacted in order; repeat until one cluster is left. The Morton curve only has to bring candidates close — the
+// merges are decided by the surface areas of real boxes, which is where an LBVH (splits decided by code bits) loses.
+//
+// Ties: a cluster prefers its "partner" position i ^ 1, then the smaller position. Every pass then merges at least
+// one pair (take the smallest union area d of the pass: if some partner pair has it, both prefer each other; if none
+// has, the smallest position a on any d-edge and the smallest b among a's d-neighbours choose each other), and
+// identical boxes (all unions equal) pair up 0-1, 2-3, ... instead of merging once per pass.
+// Node numbers are handed out downwards from n - 2, so that the last merge — the root — is node 0 like Karras' root.
+// ---------------------------------------------------------------------------
+constexpr int kPlocBlock = 256;
+constexpr int kPlocMaxRadius = 32;
+
+__global__ void ploc_init_kernel(int n, const float* __restrict__ boxes, const int32_t* __restrict__ vals, int32_t* __restrict__ cid,
+                                 float* __restrict__ cbox) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = boxes + 6 * (size_t)vals[i];
+    float* o = cbox + 6 * (size_t)i;
+    for (int a = 0; a < 6; ++a) o[a] = b[a];
+    cid[i] = ~i;
+}
+
+// nn[i] = the position in [i - r, i + r] whose box, united with box i, has the smallest area (-1 when m == 1).
+// `pair_up`: skip the search and name the partner position (the guard against a pass count that runs away).
+__global__ void __launch_bounds__(kPlocBlock) ploc_nn_kernel(int m, int r, bool pair_up, const float* __restrict__ cbox, int32_t* __restrict__ nn) {
+    __shared__ float s_box[(kPlocBlock + 2 * kPlocMaxRadius) * 6];
+    const int first = (int)blockIdx.x * kPlocBlock - r;  // position of s_box[0]
+    const int span = kPlocBlock + 2 * r;
+    for (int k = threadIdx.x; k < span * 6; k += kPlocBlock) {
+        const int pos = first + k / 6;
+        s_box[k] = (pos >= 0 && pos < m) ? cbox[6 * (size_t)pos + (k % 6)] : 0.f;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kPlocBlock + threadIdx.x;
+    if (i >= m) return;
+    if (pair_up) {
+        nn[i] = (i ^ 1) < m ? (i ^ 1) : -1;
+        return;
+    }
+    const float* me = s_box + (threadIdx.x + r) * 6;
+    const float lx = me[0], ly = me[1], lz = me[2], hx = me[3], hy = me[4], hz = me[5];
+    float best = 3.4e38f;
+    int best_j = -1;
+    const int j0 = max(i - r, 0), j1 = min(i + r, m - 1);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float* o = s_box + (j - first) * 6;
+        const float dx = fmaxf(hx, o[3]) - fminf(lx, o[0]), dy = fmaxf(hy, o[4]) - fminf(ly, o[1]), dz = fmaxf(hz, o[5]) - fminf(lz, o[2]);
+        const float area = dx * dy + dy * dz + dz * dx;
+        if (area < best || (area == best && j == (i ^ 1))) { best = area; best_j = j; }
+    }
+    nn[i] = best_j;
+}
+
+// Mutual pairs merge: the left partner makes the node and keeps the place, the right partner's place is dropped.
+__global__ void ploc_merge_kernel(int m, int n, int32_t* __restrict__ cid, float* __restrict__ cbox, const int32_t* __restrict__ nn,
+                                  unsigned int* __restrict__ n_made, int32_t* __restrict__ left, int32_t* __restrict__ right,
+                                  float* __restrict__ ibox, int32_t* __restrict__ depth, uint32_t* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nn[i];
+    uint32_t k = 1u;
+    if (j >= 0 && nn[j] == i) {
+        if (i < j) {
+            const int32_t node = n - 2 - (int32_t)atomicAdd(n_made, 1u);
+            const int32_t a = cid[i], b = cid[j];
+            float* bi = cbox + 6 * (size_t)i;
+            const float* bj = cbox + 6 * (size_t)j;
+            float u[6];
+            for (int x = 0; x < 3; ++x) { u[x] = fminf(bi[x], bj[x]); u[3 + x] = fmaxf(bi[3 + x], bj[3 + x]); }
+            float* o = ibox + 6 * (size_t)node;
+            for (int x = 0; x < 6; ++x) { o[x] = u[x]; bi[x] = u[x]; }
+            left[node] = a;
+            right[node] = b;
+            depth[node] = 1 + max(a >= 0 ? depth[a] : 0, b >= 0 ? depth[b] : 0);
+            cid[i] = node;
+        } else {
+            k = 0u;
+        }
+    }
+    keep[i] = k;
+}
+
+__global__ void ploc_compact_kernel(int m, const int32_t* __restrict__ cid, const float* __restrict__ cbox, const uint32_t* __restrict__ keep,
+                                    const uint32_t* __restrict__ pos, int32_t* __restrict__ cid_out, float* __restrict__ cbox_out,
+                                    int32_t* __restrict__ m_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (keep[i]) {
+        const uint32_t p = pos[i];
+        cid_out[p] = cid[i];
+        const float* b = cbox + 6 * (size_t)i;
+        float* o = cbox_out + 6 * (size_t)p;
+        for (int a = 0; a < 6; ++a) o[a] = b[a];
+    }
+    if (i == m - 1) *m_out = (int32_t)(pos[i] + keep[i]);
+}
+
+// Same contract as lbvh_build. radius: neighbours searched on each side (1 .. kPlocMaxRadius); passes_out: how many
+// passes the clustering took.
+inline cudaError_t ploc_build(cudaStream_t stream, int n, const float* d_boxes, const float lo[3], const float extent[3], int32_t first_record,
+                              int32_t node_base, BvhNode* d_nodes, int* depth_out, int radius, int* passes_out) {
+    const size_t un = (size_t)n;
+    cudaError_t e = cudaSuccess;
+    uint8_t* block = nullptr;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_keys = take(un * 4), o_keys2 = take(un * 4), o_vals = take(un * 4), o_vals2 = take(un * 4), o_left = take(un * 4),
+                 o_right = take(un * 4), o_ibox = take(un * 24), o_depth = take(un * 4), o_cid = take(un * 4), o_cid2 = take(un * 4),
+                 o_cbox = take(un * 24), o_cbox2 = take(un * 24), o_nn = take(un * 4), o_keep = take(un * 4), o_pos = take(un * 4),
+                 o_scalars = take(64);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, n, 0,
+                                    30, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, stream);
+    const size_t o_cub = take(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
+    if ((e = cudaMalloc(&block, off)) != cudaSuccess) return e;
+    uint32_t *keys = (uint32_t*)(block + o_keys), *keys_alt = (uint32_t*)(block + o_keys2);
+    int32_t *vals = (int32_t*)(block + o_vals), *vals_alt = (int32_t*)(block + o_vals2);
+    int32_t *left = (int32_t*)(block + o_left), *right = (int32_t*)(block + o_right), *depth = (int32_t*)(block + o_depth);
+    float* ibox = (float*)(block + o_ibox);
+    int32_t* cid[2] = {(int32_t*)(block + o_cid), (int32_t*)(block + o_cid2)};
+    float* cbox[2] = {(float*)(block + o_cbox), (float*)(block + o_cbox2)};
+    int32_t* nn = (int32_t*)(block + o_nn);
+    uint32_t *keep = (uint32_t*)(block + o_keep), *pos = (uint32_t*)(block + o_pos);
+    unsigned int* n_made = (unsigned int*)(block + o_scalars);
+    int32_t* d_m = (int32_t*)(block + o_scalars + 16);
+    void* cub_temp = block + o_cub;
+    size_t cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    const int tb = 256;
+    const int gn = (n + tb - 1) / tb;
+    const int r = radius < 1 ? 1 : (radius > kPlocMaxRadius ? kPlocMaxRadius : radius);
+    float3 flo = make_float3(lo[0], lo[1], lo[2]);
+    float3 inv = make_float3(extent[0] > 0 ? 1.f / extent[0] : 0.f, extent[1] > 0 ? 1.f / extent[1] : 0.f, extent[2] > 0 ? 1.f / extent[2] : 0.f);
+    lbvh_morton_kernel<<<gn, tb, 0, stream>>>(n, d_boxes, flo, inv, keys, vals);
+    e = cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys, keys_alt, vals, vals_alt, n, 0, 30, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(block + o_scalars, 0, 64, stream);
+    int passes = 0;
+    if (e == cudaSuccess) {
+        ploc_init_kernel<<<gn, tb, 0, stream>>>(n, d_boxes, vals_alt, cid[0], cbox[0]);
+        int m = n, cur = 0;
+        // ~40 % of the clusters merge per pass on ordinary input; past this many passes the rest is paired up blindly
+        const int patience = 96;
+        while (m > 1 && e == cudaSuccess) {
+            const int gm = (m + kPlocBlock - 1) / kPlocBlock;
+            ploc_nn_kernel<<<gm, kPlocBlock, 0, stream>>>(m, r, passes >= patience, cbox[cur], nn);
+            ploc_merge_kernel<<<gm, kPlocBlock, 0, stream>>>(m, n, cid[cur], cbox[cur], nn, n_made, left, right, ibox, depth, keep);
+            cub_bytes = scan_bytes;
+            e = cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, keep, pos, m, stream);
+            if (e != cudaSuccess) break;
+            ploc_compact_kernel<<<gm, kPlocBlock, 0, stream>>>(m, cid[cur], cbox[cur], keep, pos, cid[cur ^ 1], cbox[cur ^ 1], d_m);
+            int32_t m_new = 0;
+            e = cudaMemcpyAsync(&m_new, d_m, sizeof(m_new), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) break;
+            if (m_new >= m || m_new < 1) { e = cudaErrorUnknown; break; }  // (cannot happen: every pass merges a pair)
+            m = m_new;
+            cur ^= 1;
+            ++passes;
+        }
+        if (e == cudaSuccess) {
+            lbvh_emit_kernel<<<gn, tb, 0, stream>>>(n, d_boxes, vals_alt, left, right, ibox, node_base, first_record, d_nodes);
+            e = cudaGetLastError();
+        }
+    }
+    int32_t d = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&d, depth, sizeof(d), cudaMemcpyDeviceToHost, stream);  // node 0 is the root
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(block);
+    if (depth_out) *depth_out = d;
+    if (passes_out) *passes_out = passes;
     return e;
 }
 

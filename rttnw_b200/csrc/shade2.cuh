@@ -69,7 +69,7 @@ __device__ __forceinline__ void media_after(const SceneView& sc, const RayD& ray
 
 // kPerlinShared (RTX_PERLIN_SMEM=1, scenes with exactly one Perlin table): the 4.75 KB table — 256 gradients and the three
 // byte permutations (noise.rs:5-29) — is staged in shared memory by every CTA and NoiseTexture::value reads it there.
-template <bool kCount, bool kPerlinShared = false>
+template <bool kCount, bool kPerlinShared = false, bool kOrder = false>
 __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)) wf_shade2_kernel(WfArgs a, float4* __restrict__ accum, unsigned int* active_out,
                                                                                                    Counters* counters) {
     const unsigned FULL = 0xffffffffu;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
     PathColor pc{1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
     Sampler smp{a.k0, a.k1, 0u, 0u, 0u};
     bool fresh = false;
+    int32_t src_rec = -1;  // the record the new ray starts on (kOrder)
     if (bounce >= 0) {
         ray.o = mk(a.pool.ox[i], a.pool.oy[i], a.pool.oz[i]);
         ray.d = mk(a.pool.dx[i], a.pool.dy[i], a.pool.dz[i]);
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
             a.pool.bounce[i] = -1;
         } else {
             fresh = true;
+            src_rec = best.rec;
         }
     }
     {   // ---- refill empty slots per warp: consecutive items are the 32 pixels of one 8x4 tile at one sample index ----
@@ -156,6 +158,21 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
         a.pool.rad_r[i] = pc.rad_r; a.pool.rad_g[i] = pc.rad_g; a.pool.rad_b[i] = pc.rad_b;
         a.pool.pixel[i] = smp.pixel; a.pool.sample[i] = smp.sample;
         a.pool.bounce[i] = bounce;
+    }
+    if constexpr (kOrder) {  // this slot's place in the next trace pass (order.cuh)
+        uint2 kr = make_uint2(kOrderDead, 0u);
+        if (fresh) kr.x = order_key(a.order, src_rec, ray.d.x, ray.d.y, ray.d.z);
+        {   // one atomic per distinct key of the warp (camera rays of a refill share theirs: 32 same-address atomics
+            // per warp cost the shade pass +50 us on every scene when each lane did its own)
+            const unsigned same = __match_any_sync(FULL, kr.x);
+            const int leader = __ffs(same) - 1;
+            uint32_t base = 0;
+            if (fresh && lane == leader) base = atomicAdd(a.order.hist + kr.x, (uint32_t)__popc(same));
+            base = __shfl_sync(FULL, base, leader);
+            kr.y = base + (uint32_t)__popc(same & ((1u << lane) - 1u));
+        }
+        if (valid) a.order.key_rank[i] = kr;
+        order_scan_by_last_cta<kShadeBlock>(a.order, tid);
     }
     if (active_out) {
         const unsigned am = __ballot_sync(FULL, fresh);

@@ -97,8 +97,8 @@ class Context:
         abi.check(self.lib.rtx_ctx_sync(self.h))
 
     def set_bvh_builder(self, kind: str) -> None:
-        """'sah' (host, default) or 'lbvh' (device) for the scenes created from now on."""
-        abi.check(self.lib.rtx_ctx_set_bvh_builder(self.h, {"sah": 0, "lbvh": 1}[kind]))
+        """'sah' (host, default), 'lbvh' or 'ploc' (device) for the scenes created from now on."""
+        abi.check(self.lib.rtx_ctx_set_bvh_builder(self.h, {"sah": 0, "lbvh": 1, "ploc": 2}[kind]))
 
     def set_profiling(self, on: bool) -> None:
         abi.check(self.lib.rtx_ctx_set_profiling(self.h, 1 if on else 0))

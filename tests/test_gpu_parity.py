@@ -487,12 +487,14 @@ def test_cli_checkpoint_and_resume(tmp_path):
 # ---------------------------------------------------------------------------
 # device-side BVH construction (replaces BvhTree::new; topology is not part of the contract)
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
 @pytest.mark.parametrize("number", [1, 2, 7, 8, 9])
-def test_device_built_bvh_fixed_rays(number, earth_rgba):
-    """The same closest-hit answers whichever builder made the tree: host binned SAH or device LBVH."""
+def test_device_built_bvh_fixed_rays(number, builder, earth_rgba):
+    """The same closest-hit answers whichever builder made the tree: host binned SAH, device LBVH or device PLOC
+    (scenes 1 and 9 hold moving spheres: their boxes cover the whole shutter interval under every builder)."""
     c = R.Context(0)
     try:
-        c.set_bvh_builder("lbvh")
+        c.set_bvh_builder(builder)
         gsc = R.DeviceScene(c, R.BuiltinDesc(number))
         c.set_bvh_builder("sah")
         ref_sc = R.DeviceScene(c, R.BuiltinDesc(number))
@@ -513,10 +515,11 @@ def test_device_built_bvh_fixed_rays(number, earth_rgba):
         c.close()
 
 
-def test_device_built_bvh_random_trees_and_render():
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_device_built_bvh_random_trees_and_render(builder):
     c = R.Context(0)
     try:
-        c.set_bvh_builder("lbvh")
+        c.set_bvh_builder(builder)
         for seed in range(4):
             rng = np.random.default_rng(3000 + seed)
             desc = S.Scene(random_tree(rng)).to_desc()
@@ -671,7 +674,7 @@ def test_wide_bvh_traversal_finds_the_same_hits(number, monkeypatch):
 # round 2: the other kernel forms, the spread-out combine, NCCL behind the ABI, one process per GPU
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("form", ["RTX_TRACE=2", "RTX_TRACE=2 RTX_T_REFILL=33 RTX_T_LEAF=33 RTX_T_BURST=100000", "RTX_TRACE=3 RTX_T_BURST=4",
-                                  "RTX_TRACE=4", "RTX_SHADE=1", "RTX_PERLIN_SMEM=0"])
+                                  "RTX_TRACE=4", "RTX_SHADE=1", "RTX_PERLIN_SMEM=0", "RTX_ORDER=1", "RTX_ORDER=1 RTX_ORDER_GROUPS=4096"])
 @pytest.mark.parametrize("number", [3, 7, 9])
 def test_other_kernel_forms_trace_the_same_rays(form, number, monkeypatch, earth_rgba):
     """Every opt-in form of the trace kernel (shared-memory BVH + persistent voted warps, sorted through shared memory,

@@ -41,3 +41,18 @@ octant = (d[:, 0] > 0).astype(int) | ((d[:, 1] > 0).astype(int) << 1) | ((d[:, 2
 run(ter[np.argsort(octant, kind="stable")], "tertiary sorted by octant")
 h3 = run(ter, "tertiary again")
 run(ter[np.argsort(np.where(h3["prim_id"] < 0, 1e30, h3["t"]))], "tertiary sorted by hit distance (oracle-ish)")
+# --- round 2: order by where the ray STARTS (the primitive its parent hit), alone and with the octant ---
+src = h2["prim_id"][h2["prim_id"] >= 0]  # tertiary ray k starts on the primitive secondary ray k hit
+assert src.shape[0] == ter.shape[0]
+run(ter[np.argsort(src, kind="stable")], "tertiary sorted by source primitive")
+run(ter[np.lexsort((src, octant))], "tertiary sorted by (octant, source primitive)")
+run(ter[np.lexsort((octant, src // 4))], "tertiary sorted by (source primitive / 4, octant)")
+o = ter["origin"]
+lo, hi = np.percentile(o, 1, axis=0), np.percentile(o, 99, axis=0)
+q = np.clip(((o - lo) / np.maximum(hi - lo, 1e-30) * 1024).astype(np.int64), 0, 1023)
+def spread(v):
+    v = (v | (v << 16)) & 0x30000FF; v = (v | (v << 8)) & 0x300F00F; v = (v | (v << 4)) & 0x30C30C3; return (v | (v << 2)) & 0x9249249
+morton = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+run(ter[np.argsort(morton, kind="stable")], "tertiary sorted by origin Morton code (30 bits)")
+run(ter[np.lexsort((morton >> 12, octant))], "tertiary sorted by (octant, Morton >> 12)")
+run(ter[np.lexsort((octant, morton >> 15))], "tertiary sorted by (Morton >> 15, octant)")
