@@ -747,6 +747,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
     a.k0 = (uint32_t)p->seed; a.k1 = (uint32_t)(p->seed >> 32);
     a.tiles_x = (p->width + rtx::kTileW - 1) / rtx::kTileW;
     a.tiles_y = (p->height + rtx::kTileH - 1) / rtx::kTileH;
+    a.inv_per_block_row = 1.0f / (float)(a.tiles_x * rtx::kBlockH);
     a.n_slots = (int32_t)slots;
     a.total_items = total;
     a.next_item = c->d_next_item;
@@ -1051,6 +1052,7 @@ static int render_launch(rtx_ctx* c, const rtx_scene* s, const rtx_render_params
     a.k0 = (uint32_t)p->seed; a.k1 = (uint32_t)(p->seed >> 32);
     a.tiles_x = (p->width + rtx::kTileW - 1) / rtx::kTileW;
     a.tiles_y = (p->height + rtx::kTileH - 1) / rtx::kTileH;
+    a.inv_per_block_row = 1.0f / (float)(a.tiles_x * rtx::kBlockH);
     a.w_node = c->w_node; a.w_leaf = c->w_leaf; a.w_shade = c->w_shade;
     a.node_burst = c->node_burst;
     CU(cudaMemsetAsync(c->d_work_counter, 0, sizeof(unsigned int), c->stream));

@@ -133,9 +133,11 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
                 const unsigned long long group = item >> 5;
                 const unsigned int tile = (unsigned int)(group / (unsigned long long)a.spp_count);
                 const unsigned int smp_i = (unsigned int)(group - (unsigned long long)tile * (unsigned long long)a.spp_count);
+                int tx, ty;
+                tile_of_order(tile, a.tiles_x, a.tiles_y, a.inv_per_block_row, tx, ty);
                 const int pi = (int)(item & 31ull);
-                const int px = (int)(tile % (unsigned int)a.tiles_x) * kTileW + (pi & (kTileW - 1));
-                const int row = (int)(tile / (unsigned int)a.tiles_x) * kTileH + (pi / kTileW);  // row 0 = top
+                const int px = tx * kTileW + (pi & (kTileW - 1));
+                const int row = ty * kTileH + (pi / kTileW);  // row 0 = top
                 if (px < a.width && row < a.height) {
                     smp.pixel = (uint32_t)(row * a.width + px);
                     smp.sample = (uint32_t)a.spp_begin + smp_i;

@@ -179,6 +179,22 @@ def test_shard_spp_partitions_exactly():
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
 
 
+def test_tile_order_is_a_bijection(tmp_path):
+    """kernels.cuh's tile_of_order (the order in which the sample dispenser walks the 8x4-pixel tiles of a frame: blocks
+    of 4 x 32 tiles) and order_of_tile are inverse bijections on ragged and very large tile grids (> 2^24 tiles, where the
+    float reciprocal needs its correction step) — checked exhaustively by the host program tools/tile_order_check.cu: the
+    functions are __host__ __device__, the same code the kernels run."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    exe = tmp_path / "tile_order_check"
+    subprocess.run([nvcc, "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tools", "tile_order_check.cu")], check=True, cwd=os.path.join(ROOT, "tools"))
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "bijection on every grid tried" in out
+
+
 _GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
