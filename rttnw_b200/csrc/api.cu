@@ -77,7 +77,7 @@ struct rtx_ctx {
     int mode = 1;  // 1: wavefront (default), 0: megakernel (RTX_MODE=mega)
     // wavefront state, allocated at the first render
     void* d_pool = nullptr;
-    int pool_slots = 0, pool_slots_wanted = 1 << 19;  // 512 Ki slots x 108 B = 54 MB, in two partitions. Measured on scene 9 (M samples/s), one
+    int pool_slots = 0, pool_slots_wanted = 1 << 19;  // 512 Ki slots x 96 B = 48 MB, in two partitions. Measured on scene 9 (M samples/s), one
                                                       // stream: 512 Ki 485, 1 Mi 508, 2 Mi 516, 4 Mi 501; two streams: 256 Ki 511, 384 Ki 571,
                                                       // 512 Ki 596, 768 Ki 590, 1 Mi 582, 2 Mi 567; three / four streams at 512 Ki: 593 / 585
     unsigned long long* d_next_item = nullptr;
@@ -761,7 +761,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
         a.pool.bounce = (int32_t*)base; base += n * 4;
         a.pool.pixel = (uint32_t*)base; base += n * 4;
         a.pool.sample = (uint32_t*)base; base += n * 4;
-        float** f4[6] = {&a.pool.thr_r, &a.pool.thr_g, &a.pool.thr_b, &a.pool.rad_r, &a.pool.rad_g, &a.pool.rad_b};
+        float** f4[3] = {&a.pool.thr_r, &a.pool.thr_g, &a.pool.thr_b};
         for (auto pp : f4) { *pp = (float*)base; base += n * 4; }
     }
     CU(cudaMemsetAsync(a.pool.bounce, 0xFF, (size_t)slots * 4, c->stream));  // every slot empty (-1)
@@ -793,7 +793,7 @@ static int render_wavefront(rtx_ctx* c, const rtx_scene* s, const rtx_render_par
             for (auto pp : d8) *pp += begin;
             pt.a.pool.best_rec += begin; pt.a.pool.best_chain += begin; pt.a.pool.bounce += begin;
             pt.a.pool.pixel += begin; pt.a.pool.sample += begin;
-            float** f4[6] = {&pt.a.pool.thr_r, &pt.a.pool.thr_g, &pt.a.pool.thr_b, &pt.a.pool.rad_r, &pt.a.pool.rad_g, &pt.a.pool.rad_b};
+            float** f4[3] = {&pt.a.pool.thr_r, &pt.a.pool.thr_g, &pt.a.pool.thr_b};
             for (auto pp : f4) *pp += begin;
             if (ordered) {
                 const size_t bins = order_bins_padded(c->order_groups);

@@ -1210,7 +1210,7 @@ __global__ void __launch_bounds__(kRenderBlock) render_kernel(RenderArgs a, floa
 }
 
 // ---------------------------------------------------------------------------
-// K2w: the same path loop as a WAVEFRONT. Paths live in a pool of slots in HBM (SoA, 108 bytes per
+// K2w: the same path loop as a WAVEFRONT. Paths live in a pool of slots in HBM (SoA, 96 bytes per
 // slot, L2-resident at the default pool size); one iteration = wf_shade_kernel (every slot: shade
 // the hit found for its ray, scatter or end the path, refill empty slots with new camera rays, run
 // the medium pre-pass for the new ray) followed by wf_trace_kernel (every slot: closest surface
@@ -1221,9 +1221,9 @@ struct PathPool {
     double *ox, *oy, *oz, *dx, *dy, *dz, *time, *best_t;
     int32_t *best_rec, *best_chain, *bounce;  // bounce < 0: empty slot
     uint32_t *pixel, *sample;
-    float *thr_r, *thr_g, *thr_b, *rad_r, *rad_g, *rad_b;
+    float *thr_r, *thr_g, *thr_b;  // (no radiance: every emission ends its path — DiffuseLight never scatters, the background is a miss — so a path in flight has gathered none yet)
 };
-constexpr int kPoolBytesPerSlot = 8 * 8 + 11 * 4;
+constexpr int kPoolBytesPerSlot = 8 * 8 + 8 * 4;
 
 struct WfArgs {
     SceneView sc;
@@ -1283,7 +1283,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
         ray.d = mk(a.pool.dx[i], a.pool.dy[i], a.pool.dz[i]);
         ray.time = a.pool.time[i];
         Best best{a.pool.best_t[i], a.pool.best_rec[i], a.pool.best_chain[i]};
-        pc = PathColor{a.pool.thr_r[i], a.pool.thr_g[i], a.pool.thr_b[i], a.pool.rad_r[i], a.pool.rad_g[i], a.pool.rad_b[i]};
+        pc = PathColor{a.pool.thr_r[i], a.pool.thr_g[i], a.pool.thr_b[i], 0.f, 0.f, 0.f};
         smp.pixel = a.pool.pixel[i];
         smp.sample = a.pool.sample[i];
         smp.bounce = (uint32_t)bounce;
@@ -1348,7 +1348,6 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB * (128 / kShadeBloc
         a.pool.time[i] = ray.time;
         a.pool.best_t[i] = best.t; a.pool.best_rec[i] = best.rec; a.pool.best_chain[i] = best.chain;
         a.pool.thr_r[i] = pc.thr_r; a.pool.thr_g[i] = pc.thr_g; a.pool.thr_b[i] = pc.thr_b;
-        a.pool.rad_r[i] = pc.rad_r; a.pool.rad_g[i] = pc.rad_g; a.pool.rad_b[i] = pc.rad_b;
         a.pool.pixel[i] = smp.pixel; a.pool.sample[i] = smp.sample;
         a.pool.bounce[i] = bounce;
     }

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
         ray.d = mk(a.pool.dx[i], a.pool.dy[i], a.pool.dz[i]);
         ray.time = a.pool.time[i];
         Best best{a.pool.best_t[i], a.pool.best_rec[i], a.pool.best_chain[i]};
-        pc = PathColor{a.pool.thr_r[i], a.pool.thr_g[i], a.pool.thr_b[i], a.pool.rad_r[i], a.pool.rad_g[i], a.pool.rad_b[i]};
+        pc = PathColor{a.pool.thr_r[i], a.pool.thr_g[i], a.pool.thr_b[i], 0.f, 0.f, 0.f};
         smp.pixel = a.pool.pixel[i];
         smp.sample = a.pool.sample[i];
         smp.bounce = (uint32_t)bounce;
@@ -157,7 +157,6 @@ __global__ void __launch_bounds__(kShadeBlock, WF_SHADE_MINB*(128 / kShadeBlock)
         a.pool.time[i] = ray.time;
         a.pool.best_t[i] = 1.7976931348623157e308; a.pool.best_rec[i] = -1; a.pool.best_chain[i] = 0;
         a.pool.thr_r[i] = pc.thr_r; a.pool.thr_g[i] = pc.thr_g; a.pool.thr_b[i] = pc.thr_b;
-        a.pool.rad_r[i] = pc.rad_r; a.pool.rad_g[i] = pc.rad_g; a.pool.rad_b[i] = pc.rad_b;
         a.pool.pixel[i] = smp.pixel; a.pool.sample[i] = smp.sample;
         a.pool.bounce[i] = bounce;
     }
